@@ -1,0 +1,1163 @@
+// hssb_api.cu — C ABI, packer, level scheduler of the B200-native HSS x dense
+// product (reference path: src/matmul.jl:13-62 of bonevbs/HssMatrices.jl).
+//
+// Data flow:  builder / synthetic description  ->  BFS node table
+//             -> level-ordered generator pool in HBM (one allocation)
+//             -> task table (one GTask per small GEMM of the recursion)
+//             -> phases (leaf-up, merges by height, [exchange], translates by
+//                depth, leaf-down) launched back to back on one stream.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <functional>
+#include <memory>
+#include <new>
+
+#include "hssb_internal.h"
+#include "hssb_kernels_generic.cuh"
+#include "hssb_synth.cuh"
+#include "hssb_fast.cuh"
+
+namespace hssb {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+static inline bool is_pow2(int64_t x) { return x > 0 && (x & (x - 1)) == 0; }
+
+struct DeviceGuard {
+  int prev = -1;
+  bool ok = false;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    ok = cudaSetDevice(dev) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+
+static int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    HSSB_FAIL(HSSB_ERR_CUDA, "no CUDA device available (%s); hssb200 has no CPU fallback",
+              e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+  }
+  if (device < 0 || device >= n) HSSB_FAIL(HSSB_ERR_ARG, "device %d out of range (have %d)", device, n);
+  cudaDeviceProp prop;
+  HSSB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10)
+    HSSB_FAIL(HSSB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+              prop.minor);
+  return HSSB_OK;
+}
+
+// ----------------------------------------------------------------- builder ---
+struct BNode {
+  bool leaf = false, remote = false, used = false;
+  int64_t left = -1, right = -1;
+  int64_t m = 0, n = 0, kr = 0, kw = 0;
+  HostBlock blk[BK_COUNT];  // D,U,V (leaf) / B12,B21 (branch); R,W are filled by the parent
+};
+
+}  // namespace hssb
+
+struct hssb_builder {
+  std::vector<hssb::BNode> nodes;
+};
+
+namespace hssb {
+
+static int copy_block(HostBlock& dst, const double* src, int64_t ld, int64_t rows, int64_t cols, const char* what) {
+  dst.rows = rows;
+  dst.cols = cols;
+  dst.data.clear();
+  if (rows == 0 || cols == 0) return HSSB_OK;
+  if (!src) HSSB_FAIL(HSSB_ERR_ARG, "%s: NULL pointer for a %lld x %lld block", what, (long long)rows, (long long)cols);
+  if (ld < rows) HSSB_FAIL(HSSB_ERR_DIM, "%s: leading dimension %lld < rows %lld", what, (long long)ld, (long long)rows);
+  try {
+    dst.data.resize((size_t)(rows * cols));
+  } catch (const std::bad_alloc&) {
+    HSSB_FAIL(HSSB_ERR_ALLOC, "%s: host allocation of %lld doubles failed", what, (long long)(rows * cols));
+  }
+  for (int64_t j = 0; j < cols; ++j) memcpy(dst.data.data() + j * rows, src + j * ld, (size_t)rows * sizeof(double));
+  return HSSB_OK;
+}
+
+static void invalidate_graphs(hssb_matrix* H);
+static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st);
+
+// ------------------------------------------------------------ plan building ---
+struct BlockSource {  // per node: either host copies or nothing (synthetic)
+  const HostBlock* blk[BK_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+static void block_shape(const std::vector<Node>& nodes, const Node& t, int kind, int64_t& rows, int64_t& cols) {
+  rows = cols = 0;
+  const Node* par = t.parent >= 0 ? &nodes[(size_t)t.parent] : nullptr;
+  switch (kind) {
+    case BK_D: if (t.leaf && !t.remote) { rows = t.m; cols = t.n; } break;
+    case BK_U: if (t.leaf && !t.remote) { rows = t.m; cols = t.kr; } break;
+    case BK_V: if (t.leaf && !t.remote) { rows = t.n; cols = t.kw; } break;
+    case BK_B12: if (!t.leaf && !t.remote) { rows = nodes[(size_t)t.left].kr; cols = nodes[(size_t)t.right].kw; } break;
+    case BK_B21: if (!t.leaf && !t.remote) { rows = nodes[(size_t)t.right].kr; cols = nodes[(size_t)t.left].kw; } break;
+    case BK_R: if (par) { rows = t.kr; cols = par->kr; } break;
+    case BK_W: if (par) { rows = t.kw; cols = par->kw; } break;
+    default: break;
+  }
+}
+
+// Fills depth/height/row0/col0 (pre-order), validates the shard layout, marks
+// top / local nodes.  `nodes` must be in BFS order with node 0 the root.
+static int annotate_tree(hssb_matrix* H) {
+  auto& nodes = H->nodes;
+  const int P = H->n_shards;
+  if (!is_pow2(P)) HSSB_FAIL(HSSB_ERR_ARG, "n_shards must be a power of two, got %d", P);
+  int p = 0;
+  while ((1 << p) < P) ++p;
+  // the root acts as rooted(): no own translators (hssmatrix.jl:266)
+  nodes[0].kr = nodes[0].kw = 0;
+  nodes[0].parent = -1;
+  nodes[0].depth = 0;
+  nodes[0].row0 = nodes[0].col0 = 0;
+  int64_t maxdepth = 0;
+  for (size_t i = 0; i < nodes.size(); ++i) {  // BFS order: parents precede children
+    Node& t = nodes[i];
+    if (!t.leaf && !t.remote) {
+      Node& l = nodes[(size_t)t.left];
+      Node& r = nodes[(size_t)t.right];
+      l.parent = r.parent = (int64_t)i;
+      l.depth = r.depth = t.depth + 1;
+      l.row0 = t.row0; l.col0 = t.col0;
+      r.row0 = t.row0 + l.m; r.col0 = t.col0 + l.n;
+      if (l.m + r.m != t.m || l.n + r.n != t.n)
+        HSSB_FAIL(HSSB_ERR_DIM, "node %zu: children sizes do not add up", i);
+    }
+    maxdepth = std::max<int64_t>(maxdepth, t.depth);
+  }
+  H->depth = maxdepth;
+  for (size_t i = nodes.size(); i-- > 0;) {
+    Node& t = nodes[i];
+    t.height = (t.leaf || t.remote) ? 0 : 1 + std::max(nodes[(size_t)t.left].height, nodes[(size_t)t.right].height);
+  }
+  // shard layout
+  std::vector<int64_t> cut;  // nodes at depth p, left to right (BFS keeps that order)
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    Node& t = nodes[i];
+    t.top = t.depth < p;
+    if (t.top && (t.leaf || t.remote))
+      HSSB_FAIL(HSSB_ERR_ARG, "tree too shallow for %d shards: node %zu at depth %d is a leaf", P, i, t.depth);
+    if (t.depth == p) cut.push_back((int64_t)i);
+  }
+  if ((int)cut.size() != P) HSSB_FAIL(HSSB_ERR_ARG, "expected %d subtrees at depth %d, found %zu", P, p, cut.size());
+  if (H->shard_rank < 0 || H->shard_rank >= P) HSSB_FAIL(HSSB_ERR_ARG, "shard_rank %d out of range", H->shard_rank);
+  for (int g = 0; g < P; ++g) {
+    const Node& t = nodes[(size_t)cut[(size_t)g]];
+    if (g == H->shard_rank ? t.remote : !t.remote)
+      HSSB_FAIL(HSSB_ERR_ARG, "subtree %d at the shard cut must be %s on shard %d", g,
+                g == H->shard_rank ? "local" : "a remote placeholder", H->shard_rank);
+  }
+  const Node& lr = nodes[(size_t)cut[(size_t)H->shard_rank]];
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    Node& t = nodes[i];
+    t.local = !t.top && !t.remote;
+    if (t.remote && t.depth != p) HSSB_FAIL(HSSB_ERR_ARG, "remote placeholder %zu is not at the shard cut", i);
+  }
+  H->m = nodes[0].m; H->n = nodes[0].n;
+  H->local_m = lr.m; H->local_n = lr.n;
+  H->local_row0 = lr.row0; H->local_col0 = lr.col0;
+  return HSSB_OK;
+}
+
+static bool on_root_path(const std::vector<Node>& nodes, int64_t node, int64_t local_root) {
+  // true if `node` is an ancestor-or-self of local_root
+  for (int64_t t = local_root; t >= 0; t = nodes[(size_t)t].parent)
+    if (t == node) return true;
+  return false;
+}
+
+// Assigns pool offsets in level order:
+//   [leaf D][leaf U][leaf V] then per depth (deepest first) [B12][B21][R][W].
+// Every block starts on a 128-byte boundary and has an even leading dimension
+// so that any column is 16-byte aligned (vector loads / bulk copies).
+static void layout_pool(hssb_matrix* H) {
+  auto& nodes = H->nodes;
+  int64_t off = 0, gen = 0;
+  auto place = [&](Node& t, int kind) {
+    int64_t rows, cols;
+    block_shape(nodes, t, kind, rows, cols);
+    t.rows[kind] = rows; t.cols[kind] = cols;
+    if (rows == 0 || cols == 0) { t.off[kind] = -1; t.ld[kind] = (int32_t)std::max<int64_t>(round_up(rows, 2), 2); return; }
+    t.ld[kind] = (int32_t)round_up(rows, 2);
+    t.off[kind] = off;
+    off += round_up((int64_t)t.ld[kind] * cols, 16);
+    gen += rows * cols;
+  };
+  const int leaf_kinds[3] = {BK_D, BK_U, BK_V};
+  for (int kk = 0; kk < 3; ++kk)
+    for (int64_t li : H->leaves) place(nodes[(size_t)li], leaf_kinds[kk]);
+  const int lvl_kinds[4] = {BK_B12, BK_B21, BK_R, BK_W};
+  for (int64_t d = H->depth; d >= 0; --d)
+    for (int kk = 0; kk < 4; ++kk)
+      for (auto& t : nodes)
+        if (t.depth == d) place(t, lvl_kinds[kk]);
+  H->pool_len = std::max<int64_t>(off, 16);
+  H->gen_elems = gen;
+}
+
+static void layout_workspace(hssb_matrix* H) {
+  auto& nodes = H->nodes;
+  const int P = H->n_shards;
+  int p = 0;
+  while ((1 << p) < P) ++p;
+  int64_t zo = 0, fo = 0;
+  // exchange slots first (depth-p nodes in rank order, equal slot size)
+  if (P > 1) {
+    int64_t slot = 0;
+    for (auto& t : nodes)
+      if (t.depth == p) slot = std::max<int64_t>(slot, round_up(t.kw, 2));
+    H->xchg_zoff = 0;
+    H->xchg_slot_rows = slot;
+    for (auto& t : nodes)
+      if (t.depth == p) { t.zoff = zo; t.ldz = (int32_t)std::max<int64_t>(round_up(t.kw, 2), 2); zo += slot; }
+  }
+  for (size_t i = 1; i < nodes.size(); ++i) {  // BFS order keeps siblings adjacent
+    Node& t = nodes[i];
+    if (t.zoff < 0) { t.zoff = zo; t.ldz = (int32_t)std::max<int64_t>(round_up(t.kw, 2), 2); zo += round_up(t.kw, 2); }
+    t.foff = fo; t.ldf = (int32_t)std::max<int64_t>(round_up(t.kr, 2), 2); fo += round_up(t.kr, 2);
+  }
+  H->z_rows = std::max<int64_t>(zo, 2);
+  H->f_rows = std::max<int64_t>(fo, 2);
+}
+
+static void add_phase(hssb_matrix* H, int kind, int level, bool top, std::vector<GTask>& batch) {
+  if (batch.empty()) return;
+  Phase ph;
+  ph.kind = kind; ph.level = level; ph.top = top;
+  ph.task0 = (int64_t)H->tasks_host.size();
+  ph.ntasks = (int64_t)batch.size();
+  for (auto& t : batch) { ph.maxM = std::max(ph.maxM, t.M); H->flops_per_rhs += 2ll * t.M * ((int64_t)t.K0 + t.K1); }
+  H->tasks_host.insert(H->tasks_host.end(), batch.begin(), batch.end());
+  H->phases.push_back(ph);
+  batch.clear();
+}
+
+static void build_plan(hssb_matrix* H) {
+  auto& nodes = H->nodes;
+  const int P = H->n_shards;
+  int p = 0;
+  while ((1 << p) < P) ++p;
+  int64_t local_root = 0;
+  for (size_t i = 0; i < nodes.size(); ++i)
+    if (nodes[i].depth == p && !nodes[i].remote) local_root = (int64_t)i;
+  const int64_t r0 = H->local_row0, c0 = H->local_col0;
+  std::vector<GTask> batch;
+  auto blank = []() { GTask t; memset(&t, 0, sizeof(t)); t.lda0 = t.lda1 = t.ldb0 = t.ldb1 = t.ldc = 2; return t; };
+
+  // ---- leaf up: Z = V' X (matmul.jl:34); skipped for a root leaf and for kw == 0
+  for (int64_t li : H->leaves) {
+    const Node& t = nodes[(size_t)li];
+    if (t.parent < 0 || t.kw == 0) continue;
+    GTask g = blank();
+    g.a0 = t.off[BK_V]; g.lda0 = t.ld[BK_V]; g.ta0 = 1;
+    g.sb0 = SRC_X; g.b0 = t.col0 - c0;
+    g.M = (int32_t)t.kw; g.K0 = (int32_t)t.n; g.K1 = 0;
+    g.sc = SRC_Z; g.c = t.zoff; g.ldc = t.ldz;
+    batch.push_back(g);
+  }
+  add_phase(H, PH_LEAF_UP, 0, false, batch);
+
+  // ---- merges: Z = W1' Z1 + W2' Z2 (matmul.jl:39), never for the root (W is k x 0)
+  auto merge_task = [&](const Node& t) {
+    const Node& l = nodes[(size_t)t.left];
+    const Node& r = nodes[(size_t)t.right];
+    GTask g = blank();
+    g.a0 = l.off[BK_W]; g.lda0 = l.ld[BK_W]; g.ta0 = 1; g.sb0 = SRC_Z; g.b0 = l.zoff; g.ldb0 = l.ldz; g.K0 = (int32_t)l.kw;
+    g.a1 = r.off[BK_W]; g.lda1 = r.ld[BK_W]; g.ta1 = 1; g.sb1 = SRC_Z; g.b1 = r.zoff; g.ldb1 = r.ldz; g.K1 = (int32_t)r.kw;
+    g.M = (int32_t)t.kw;
+    g.sc = SRC_Z; g.c = t.zoff; g.ldc = t.ldz;
+    return g;
+  };
+  const int max_h = nodes[0].height;
+  for (int h = 1; h <= max_h; ++h) {
+    for (auto& t : nodes)
+      if (t.local && !t.leaf && t.height == h && t.parent >= 0 && t.kw > 0) batch.push_back(merge_task(t));
+    add_phase(H, PH_MERGE, h, false, batch);
+  }
+  if (P > 1) {
+    Phase ph; ph.kind = PH_EXCHANGE; H->phases.push_back(ph);
+    for (int d = p - 1; d >= 1; --d) {  // top tree, bottom-up; only nodes OFF the root->local path feed a local F
+      for (size_t i = 0; i < nodes.size(); ++i) {
+        const Node& t = nodes[i];
+        if (t.top && t.depth == d && t.kw > 0 && !on_root_path(nodes, (int64_t)i, local_root)) batch.push_back(merge_task(t));
+      }
+      add_phase(H, PH_MERGE, d, true, batch);
+    }
+  }
+
+  // ---- translates: F1 = B12 Z2 (+ R1 F), F2 = B21 Z1 (+ R2 F) (matmul.jl:51-57)
+  auto translate_tasks = [&](const Node& t, bool only_path) {
+    const Node& l = nodes[(size_t)t.left];
+    const Node& r = nodes[(size_t)t.right];
+    const bool has_f = t.parent >= 0 && t.kr > 0;
+    for (int side = 0; side < 2; ++side) {
+      const Node& c = side ? r : l;   // child receiving F
+      const Node& s = side ? l : r;   // sibling providing Z
+      const int64_t ci = side ? t.right : t.left;
+      if (c.kr == 0) continue;
+      if (only_path && !on_root_path(nodes, ci, local_root)) continue;
+      if (c.remote) continue;
+      GTask g = blank();
+      const int bk = side ? BK_B21 : BK_B12;
+      g.a0 = t.off[bk]; g.lda0 = t.ld[bk]; g.ta0 = 0; g.sb0 = SRC_Z; g.b0 = s.zoff; g.ldb0 = s.ldz; g.K0 = (int32_t)s.kw;
+      if (has_f) { g.a1 = c.off[BK_R]; g.lda1 = c.ld[BK_R]; g.ta1 = 0; g.sb1 = SRC_F; g.b1 = t.foff; g.ldb1 = t.ldf; g.K1 = (int32_t)t.kr; }
+      g.M = (int32_t)c.kr;
+      g.sc = SRC_F; g.c = c.foff; g.ldc = c.ldf;
+      if (g.a0 < 0) g.K0 = 0;
+      if (g.a1 < 0) g.K1 = 0;
+      batch.push_back(g);
+    }
+  };
+  for (int d = 0; d < p; ++d) {
+    for (auto& t : nodes)
+      if (t.top && t.depth == d) translate_tasks(t, true);
+    add_phase(H, PH_TRANSLATE, d, true, batch);
+  }
+  for (int d = p; d <= (int)H->depth; ++d) {
+    for (auto& t : nodes)
+      if (t.local && !t.leaf && t.depth == d) translate_tasks(t, false);
+    add_phase(H, PH_TRANSLATE, d, false, batch);
+  }
+
+  // ---- leaf down: Y = alpha (D X + U F) + beta Y (matmul.jl:46-47; :21-22 for a root leaf)
+  for (int64_t li : H->leaves) {
+    const Node& t = nodes[(size_t)li];
+    GTask g = blank();
+    g.a0 = t.off[BK_D]; g.lda0 = t.ld[BK_D]; g.sb0 = SRC_X; g.b0 = t.col0 - c0; g.K0 = (int32_t)t.n;
+    if (t.parent >= 0 && t.kr > 0) { g.a1 = t.off[BK_U]; g.lda1 = t.ld[BK_U]; g.sb1 = SRC_F; g.b1 = t.foff; g.ldb1 = t.ldf; g.K1 = (int32_t)t.kr; }
+    g.M = (int32_t)t.m;
+    g.sc = SRC_Y; g.c = t.row0 - r0; g.epilogue = 1;
+    if (g.a0 < 0) g.K0 = 0;
+    if (g.M > 0) batch.push_back(g);
+  }
+  add_phase(H, PH_LEAF_DOWN, 0, false, batch);
+}
+
+static void detect_uniform(hssb_matrix* H) {
+  // Fast fixed-shape kernels need: a perfect local tree, square leaves of one
+  // size, one rank everywhere (rows and columns).
+  H->uniform = false;
+  if (H->leaves.empty()) return;
+  const Node& l0 = H->nodes[(size_t)H->leaves[0]];
+  if (l0.parent < 0) return;
+  const int64_t m = l0.m, r = l0.kr;
+  if (m != l0.n || r != l0.kw || r <= 0) return;
+  for (auto& t : H->nodes) {
+    if (t.parent < 0) continue;
+    if (t.kr != r || t.kw != r) return;
+    if (t.leaf && !t.remote && (t.m != m || t.n != m || t.depth != H->depth)) return;
+  }
+  H->uniform = true;
+  H->uni_m = m;
+  H->uni_r = r;
+}
+
+// Common tail of finalize / create_synthetic once H->nodes is filled (BFS order).
+// Host-only part: tree annotation, pool / workspace layout, task table, phases.
+static int plan_matrix(hssb_matrix* H) {
+  int rc = annotate_tree(H);
+  if (rc) return rc;
+  auto& nodes = H->nodes;
+  // local leaves left to right = pre-order walk
+  {
+    std::vector<int64_t> stack{0};
+    while (!stack.empty()) {
+      const int64_t i = stack.back();
+      stack.pop_back();
+      const Node& t = nodes[(size_t)i];
+      if (t.remote) continue;
+      if (t.leaf) { H->leaves.push_back(i); continue; }
+      stack.push_back(t.right);
+      stack.push_back(t.left);
+    }
+  }
+  for (auto& t : nodes) {
+    if (t.leaf && !t.remote) {
+      H->max_leaf_m = std::max(H->max_leaf_m, t.m);
+      H->max_leaf_n = std::max(H->max_leaf_n, t.n);
+    }
+    H->max_rank = std::max(H->max_rank, std::max(t.kr, t.kw));
+  }
+  layout_pool(H);
+  layout_workspace(H);
+  build_plan(H);
+  detect_uniform(H);
+  plan_fast_phases(H);
+
+  return HSSB_OK;
+}
+
+// Device part: allocate the pool, upload (or generate) the generators and the task table.
+static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src) {
+  int rc = plan_matrix(H);
+  if (rc) return rc;
+  auto& nodes = H->nodes;
+  DeviceGuard dg(H->device);
+  if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", H->device);
+  HSSB_CUDA(cudaStreamCreateWithFlags(&H->stream, cudaStreamNonBlocking));
+  if (cudaMalloc(&H->pool_dev, (size_t)H->pool_len * sizeof(double)) != cudaSuccess) {
+    cudaGetLastError();
+    HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of the %.3f GB generator pool failed", H->pool_len * 8e-9);
+  }
+  HSSB_CUDA(cudaMemsetAsync(H->pool_dev, 0, (size_t)H->pool_len * sizeof(double), H->stream));
+  if (!H->tasks_host.empty()) {
+    HSSB_CUDA(cudaMalloc(&H->tasks_dev, H->tasks_host.size() * sizeof(GTask)));
+    HSSB_CUDA(cudaMemcpyAsync(H->tasks_dev, H->tasks_host.data(), H->tasks_host.size() * sizeof(GTask),
+                              cudaMemcpyHostToDevice, H->stream));
+  }
+  if (src) {
+    // host generators: assemble in pinned chunks and upload
+    const size_t CH = (size_t)1 << 22;  // 32 MiB of doubles per chunk
+    double* stage[2] = {nullptr, nullptr};
+    cudaEvent_t ev[2];
+    for (int i = 0; i < 2; ++i) {
+      HSSB_CUDA(cudaMallocHost(&stage[i], CH * sizeof(double)));
+      HSSB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
+    }
+    struct Piece { int64_t off; const HostBlock* hb; int32_t ld; };
+    std::vector<Piece> pieces;
+    for (size_t i = 0; i < nodes.size(); ++i)
+      for (int k = 0; k < BK_COUNT; ++k)
+        if (nodes[i].off[k] >= 0) pieces.push_back({nodes[i].off[k], (*src)[i].blk[k], nodes[i].ld[k]});
+    std::sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) { return a.off < b.off; });
+    size_t pi = 0;
+    int cur = 0;
+    while (pi < pieces.size()) {
+      const int64_t base = pieces[pi].off;
+      HSSB_CUDA(cudaEventSynchronize(ev[cur]));
+      size_t pj = pi;
+      int64_t end = base;
+      memset(stage[cur], 0, CH * sizeof(double));
+      while (pj < pieces.size()) {
+        const Piece& pc = pieces[pj];
+        const int64_t pend = pc.off + (int64_t)pc.ld * pc.hb->cols;
+        if (pend - base > (int64_t)CH) break;
+        for (int64_t j = 0; j < pc.hb->cols; ++j)
+          memcpy(stage[cur] + (pc.off - base) + j * pc.ld, pc.hb->data.data() + j * pc.hb->rows,
+                 (size_t)pc.hb->rows * sizeof(double));
+        end = pend;
+        ++pj;
+      }
+      if (pj == pi) {  // single block larger than a chunk: upload it column by column
+        const Piece& pc = pieces[pi];
+        HSSB_CUDA(cudaMemcpy2DAsync(H->pool_dev + pc.off, (size_t)pc.ld * 8, pc.hb->data.data(), (size_t)pc.hb->rows * 8,
+                                    (size_t)pc.hb->rows * 8, (size_t)pc.hb->cols, cudaMemcpyHostToDevice, H->stream));
+        HSSB_CUDA(cudaStreamSynchronize(H->stream));
+        ++pi;
+        continue;
+      }
+      HSSB_CUDA(cudaMemcpyAsync(H->pool_dev + base, stage[cur], (size_t)(end - base) * sizeof(double),
+                                cudaMemcpyHostToDevice, H->stream));
+      HSSB_CUDA(cudaEventRecord(ev[cur], H->stream));
+      cur ^= 1;
+      pi = pj;
+    }
+    HSSB_CUDA(cudaStreamSynchronize(H->stream));
+    for (int i = 0; i < 2; ++i) { cudaFreeHost(stage[i]); cudaEventDestroy(ev[i]); }
+  } else {
+    // synthetic generators, produced on the device
+    std::vector<SynthBlock> sb;
+    const double tscale = H->synth_rank > 0 ? 1.0 / sqrt(2.0 * (double)H->synth_rank) : 1.0;
+    for (auto& t : nodes)
+      for (int k = 0; k < BK_COUNT; ++k)
+        if (t.off[k] >= 0) {
+          SynthBlock b;
+          b.off = t.off[k];
+          b.key = synth_key(H->seed, t.heap_id, k);
+          b.rows = (int32_t)t.rows[k]; b.cols = (int32_t)t.cols[k]; b.ld = t.ld[k];
+          b.c = IH4_SCALE * ((k == BK_R || k == BK_W) ? tscale : 1.0);
+          sb.push_back(b);
+        }
+    if (!sb.empty()) {
+      SynthBlock* dsb = nullptr;
+      HSSB_CUDA(cudaMalloc(&dsb, sb.size() * sizeof(SynthBlock)));
+      HSSB_CUDA(cudaMemcpyAsync(dsb, sb.data(), sb.size() * sizeof(SynthBlock), cudaMemcpyHostToDevice, H->stream));
+      const int grid = (int)std::min<size_t>(sb.size(), 148 * 16);
+      synth_fill_kernel<<<grid, 256, 0, H->stream>>>(dsb, (int64_t)sb.size(), H->pool_dev);
+      HSSB_CUDA(cudaGetLastError());
+      HSSB_CUDA(cudaStreamSynchronize(H->stream));
+      cudaFree(dsb);
+    }
+  }
+  HSSB_CUDA(cudaStreamSynchronize(H->stream));
+  return HSSB_OK;
+}
+
+static int ensure_workspace(hssb_matrix* H, int64_t nrhs) {
+  if (nrhs <= H->ws_nrhs) return HSSB_OK;
+  if (H->z_dev) cudaFree(H->z_dev);
+  if (H->f_dev) cudaFree(H->f_dev);
+  H->z_dev = H->f_dev = nullptr;
+  H->ws_nrhs = 0;
+  const size_t zb = (size_t)H->z_rows * (size_t)nrhs * sizeof(double);
+  const size_t fb = (size_t)H->f_rows * (size_t)nrhs * sizeof(double);
+  if (cudaMalloc(&H->z_dev, zb) != cudaSuccess || cudaMalloc(&H->f_dev, fb) != cudaSuccess) {
+    cudaGetLastError();
+    HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of the Z/F workspaces (%.3f GB) failed", (zb + fb) * 1e-9);
+  }
+  H->ws_nrhs = nrhs;
+  invalidate_graphs(H);
+  return HSSB_OK;
+}
+
+// BFS renumbering of the builder's post-order ids; node 0 becomes the root.
+static void nodes_from_builder(const hssb_builder* b, int64_t root, hssb_matrix* H, std::vector<BlockSource>& src) {
+  std::vector<int64_t> order{root};
+  for (size_t q = 0; q < order.size(); ++q) {
+    const BNode& bn = b->nodes[(size_t)order[q]];
+    if (!bn.leaf && !bn.remote) { order.push_back(bn.left); order.push_back(bn.right); }
+  }
+  std::vector<int64_t> newid(b->nodes.size(), -1);
+  for (size_t q = 0; q < order.size(); ++q) newid[(size_t)order[q]] = (int64_t)q;
+  H->nodes.resize(order.size());
+  src.resize(order.size());
+  for (size_t q = 0; q < order.size(); ++q) {
+    const BNode& bn = b->nodes[(size_t)order[q]];
+    Node& t = H->nodes[q];
+    t.leaf = bn.leaf; t.remote = bn.remote;
+    t.m = bn.m; t.n = bn.n; t.kr = bn.kr; t.kw = bn.kw;
+    if (!bn.leaf && !bn.remote) { t.left = newid[(size_t)bn.left]; t.right = newid[(size_t)bn.right]; }
+    for (int k = 0; k < BK_COUNT; ++k) src[q].blk[k] = &bn.blk[k];
+  }
+}
+
+// BFS construction of the bisection tree (clustertree.jl:27-35): split while len > leafsize,
+// left child gets ceil(len/2).  Subtrees at the shard cut owned by other ranks become placeholders.
+static void nodes_synthetic(hssb_matrix* H, int64_t n, int64_t leafsize, int64_t rank) {
+  int p = 0;
+  while ((1 << p) < H->n_shards) ++p;
+  struct Item { int64_t len; uint64_t heap; int depth; int64_t pos; };
+  std::vector<Item> items{{n, 1, 0, 0}};
+  H->nodes.resize(1);
+  for (size_t q = 0; q < items.size(); ++q) {
+    const Item it = items[q];
+    Node& t = H->nodes[q];
+    t.m = t.n = it.len;
+    t.kr = t.kw = (q == 0) ? 0 : rank;
+    t.heap_id = it.heap;
+    const bool remote = (it.depth == p && H->n_shards > 1 && it.pos != H->shard_rank);
+    if (remote) { t.remote = true; continue; }
+    if (it.len > leafsize) {
+      const int64_t nl = (it.len + 1) / 2;
+      t.leaf = false;
+      t.left = (int64_t)items.size();
+      t.right = t.left + 1;
+      items.push_back({nl, 2 * it.heap, it.depth + 1, 2 * it.pos});
+      items.push_back({it.len - nl, 2 * it.heap + 1, it.depth + 1, 2 * it.pos + 1});
+      H->nodes.resize(items.size());
+    } else {
+      H->nodes[q].leaf = true;
+    }
+  }
+}
+
+// Host image of the packed pool (plan-only handles used by the CPU tests).
+static void fill_pool_host(hssb_matrix* H, const std::vector<BlockSource>* src) {
+  H->pool_host.assign((size_t)H->pool_len, 0.0);
+  const double tscale = H->synth_rank > 0 ? 1.0 / sqrt(2.0 * (double)H->synth_rank) : 1.0;
+  for (size_t i = 0; i < H->nodes.size(); ++i) {
+    const Node& t = H->nodes[i];
+    for (int k = 0; k < BK_COUNT; ++k) {
+      if (t.off[k] < 0) continue;
+      double* dst = H->pool_host.data() + t.off[k];
+      if (src) {
+        const HostBlock* hb = (*src)[i].blk[k];
+        for (int64_t j = 0; j < t.cols[k]; ++j)
+          memcpy(dst + j * t.ld[k], hb->data.data() + j * hb->rows, (size_t)t.rows[k] * sizeof(double));
+      } else {
+        const uint64_t key = synth_key(H->seed, t.heap_id, k);
+        const double c = IH4_SCALE * ((k == BK_R || k == BK_W) ? tscale : 1.0);
+        for (int64_t j = 0; j < t.cols[k]; ++j)
+          for (int64_t r = 0; r < t.rows[k]; ++r) dst[j * t.ld[k] + r] = synth_value(key, (uint64_t)(j * t.rows[k] + r), c);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------- NCCL glue ---
+// Loaded lazily with dlopen so that single-GPU use never needs NCCL.
+struct Id128 { char b[128]; };
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ Id128, int) = nullptr;
+  int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+static NcclApi g_nccl;
+
+static int load_nccl() {
+  if (g_nccl.lib) return HSSB_OK;
+  const char* names[] = {"libnccl.so.2", "libnccl.so"};
+  void* lib = nullptr;
+  for (const char* nm : names) {
+    lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+    if (lib) break;
+  }
+  if (!lib) HSSB_FAIL(HSSB_ERR_COMM, "cannot dlopen libnccl.so.2: %s", dlerror());
+  g_nccl.GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+  g_nccl.CommInitRank = (int (*)(void**, int, Id128, int))dlsym(lib, "ncclCommInitRank");
+  g_nccl.AllGather = (int (*)(const void*, void*, size_t, int, void*, cudaStream_t))dlsym(lib, "ncclAllGather");
+  g_nccl.CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+  g_nccl.GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+  if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy)
+    HSSB_FAIL(HSSB_ERR_COMM, "libnccl is missing required symbols");
+  g_nccl.lib = lib;
+  return HSSB_OK;
+}
+#define HSSB_NCCL(expr)                                                                                   \
+  do {                                                                                                    \
+    int _r = (expr);                                                                                      \
+    if (_r != 0)                                                                                          \
+      HSSB_FAIL(HSSB_ERR_COMM, "NCCL error %d (%s) at %s:%d", _r,                                         \
+                g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?", __FILE__, __LINE__);             \
+  } while (0)
+
+// ------------------------------------------------------------------ launch ---
+static int launch_generic(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
+  if (ph.ntasks == 0) return HSSB_OK;
+  dim3 grid((unsigned)ph.ntasks, (unsigned)((ph.maxM + G_TM - 1) / G_TM), (unsigned)((cp.nrhs + G_TN - 1) / G_TN));
+  generic_level_kernel<<<grid, G_THREADS, 0, st>>>(H->tasks_dev + ph.task0, cp);
+  H->launches++;
+  HSSB_CUDA(cudaGetLastError());
+  return HSSB_OK;
+}
+
+static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
+  const bool prof = H->profile;
+  if (prof) {
+    while (H->prof_events.size() < H->phases.size() + 1) {
+      cudaEvent_t e;
+      HSSB_CUDA(cudaEventCreate(&e));
+      H->prof_events.push_back(e);
+    }
+    HSSB_CUDA(cudaEventRecord(H->prof_events[0], st));
+    H->prof_nrhs = cp.nrhs;
+  }
+  size_t pi = 0;
+  for (const Phase& ph : H->phases) {
+    ++pi;
+    struct Rec {
+      hssb_matrix* H; cudaStream_t st; size_t i; bool on;
+      ~Rec() { if (on) cudaEventRecord(H->prof_events[i], st); }
+    } rec{H, st, pi, prof};
+    if (ph.kind == PH_EXCHANGE) {
+      if (!H->nccl_comm) HSSB_FAIL(HSSB_ERR_STATE, "sharded matrix: call hssb_comm_init before hssb_matmul");
+      double* buf = cp.Z + H->xchg_zoff * (int64_t)cp.nrhs;
+      const size_t count = (size_t)H->xchg_slot_rows * (size_t)cp.nrhs;
+      HSSB_NCCL(g_nccl.AllGather(buf + (size_t)H->shard_rank * count, buf, count, /*ncclDouble*/ 8, H->nccl_comm, st));
+      continue;
+    }
+    int rc;
+    if (ph.fast && !H->force_generic && fast_phase_supported(H, ph, cp))
+      rc = launch_fast(H, ph, cp, st);
+    else
+      rc = launch_generic(H, ph, cp, st);
+    if (rc) return rc;
+  }
+  return HSSB_OK;
+}
+
+// -------------------------------------------------------------- CUDA graphs ---
+// The level schedule is 2*depth+2 dependent launches of a few microseconds
+// each; replaying it as one graph removes the per-launch CPU cost.
+static void invalidate_graphs(hssb_matrix* H) {
+  for (auto& g : H->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  H->graphs.clear();
+}
+
+static bool same_call(const CallParams& a, const CallParams& b) {
+  return a.pool == b.pool && a.X == b.X && a.Y == b.Y && a.Z == b.Z && a.F == b.F && a.ldx == b.ldx && a.ldy == b.ldy &&
+         a.nrhs == b.nrhs && a.alpha == b.alpha && a.beta == b.beta;
+}
+
+static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
+  for (auto& g : H->graphs)
+    if (same_call(g.cp, cp)) {
+      HSSB_CUDA(cudaGraphLaunch(g.exec, st));
+      H->launches += g.kernels;
+      return HSSB_OK;
+    }
+  if (H->graphs.size() >= 16) invalidate_graphs(H);
+  cudaGraph_t graph = nullptr;
+  const int64_t before = H->launches;
+  HSSB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = run_phases(H, cp, st);
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  const int64_t kernels = H->launches - before;
+  H->launches = before;
+  if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+  if (e != cudaSuccess) { cudaGetLastError(); HSSB_FAIL(HSSB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e)); }
+  hssb_matrix::GraphSlot slot;
+  slot.cp = cp;
+  slot.kernels = kernels;
+  e = cudaGraphInstantiate(&slot.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { cudaGetLastError(); HSSB_FAIL(HSSB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+  H->graphs.push_back(slot);
+  HSSB_CUDA(cudaGraphLaunch(slot.exec, st));
+  H->launches += kernels;
+  return HSSB_OK;
+}
+
+}  // namespace hssb
+
+using namespace hssb;
+
+// =============================================================== C ABI =====
+extern "C" {
+
+int hssb_version(void) { return HSSB_VERSION; }
+const char* hssb_last_error(void) { return g_err; }
+
+int hssb_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  int ok = 0;
+  for (int i = 0; i < n; ++i) {
+    cudaDeviceProp p;
+    if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
+  }
+  return ok;
+}
+
+int hssb_builder_create(hssb_builder** out) {
+  if (!out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_builder_create: out is NULL");
+  *out = new (std::nothrow) hssb_builder();
+  if (!*out) HSSB_FAIL(HSSB_ERR_ALLOC, "hssb_builder_create: out of memory");
+  return HSSB_OK;
+}
+
+void hssb_builder_destroy(hssb_builder* b) { delete b; }
+
+int64_t hssb_builder_add_leaf(hssb_builder* b, int64_t m, int64_t n, int64_t kr, int64_t kw, const double* D, int64_t ldd,
+                              const double* U, int64_t ldu, const double* V, int64_t ldv) {
+  if (!b) HSSB_FAIL(HSSB_ERR_ARG, "add_leaf: builder is NULL");
+  if (m < 0 || n < 0 || kr < 0 || kw < 0) HSSB_FAIL(HSSB_ERR_ARG, "add_leaf: negative size");
+  if (m > INT32_MAX || n > INT32_MAX || kr > INT32_MAX || kw > INT32_MAX) HSSB_FAIL(HSSB_ERR_ARG, "add_leaf: block too large");
+  BNode nd;
+  nd.leaf = true; nd.m = m; nd.n = n; nd.kr = kr; nd.kw = kw;
+  int rc;
+  if ((rc = copy_block(nd.blk[BK_D], D, ldd, m, n, "add_leaf D"))) return rc;
+  if ((rc = copy_block(nd.blk[BK_U], U, ldu, m, kr, "add_leaf U"))) return rc;  // rows(U) == rows(D): hssmatrix.jl:41
+  if ((rc = copy_block(nd.blk[BK_V], V, ldv, n, kw, "add_leaf V"))) return rc;  // rows(V) == cols(D): hssmatrix.jl:42
+  b->nodes.push_back(std::move(nd));
+  return (int64_t)b->nodes.size() - 1;
+}
+
+int64_t hssb_builder_add_remote(hssb_builder* b, int64_t m, int64_t n, int64_t kr, int64_t kw) {
+  if (!b) HSSB_FAIL(HSSB_ERR_ARG, "add_remote: builder is NULL");
+  if (m < 0 || n < 0 || kr < 0 || kw < 0) HSSB_FAIL(HSSB_ERR_ARG, "add_remote: negative size");
+  BNode nd;
+  nd.remote = true; nd.m = m; nd.n = n; nd.kr = kr; nd.kw = kw;
+  b->nodes.push_back(std::move(nd));
+  return (int64_t)b->nodes.size() - 1;
+}
+
+int64_t hssb_builder_add_branch(hssb_builder* b, int64_t left, int64_t right, int64_t kr, int64_t kw, const double* B12,
+                                int64_t ldb12, const double* B21, int64_t ldb21, const double* R1, int64_t ldr1,
+                                const double* W1, int64_t ldw1, const double* R2, int64_t ldr2, const double* W2,
+                                int64_t ldw2) {
+  if (!b) HSSB_FAIL(HSSB_ERR_ARG, "add_branch: builder is NULL");
+  const int64_t nn = (int64_t)b->nodes.size();
+  if (left < 0 || left >= nn || right < 0 || right >= nn || left == right)
+    HSSB_FAIL(HSSB_ERR_ARG, "add_branch: invalid child ids %lld, %lld", (long long)left, (long long)right);
+  if (b->nodes[(size_t)left].used || b->nodes[(size_t)right].used)
+    HSSB_FAIL(HSSB_ERR_ARG, "add_branch: a child already has a parent");
+  if (kr < 0 || kw < 0 || kr > INT32_MAX || kw > INT32_MAX) HSSB_FAIL(HSSB_ERR_ARG, "add_branch: bad gensize");
+  BNode nd;
+  nd.leaf = false; nd.left = left; nd.right = right; nd.kr = kr; nd.kw = kw;
+  BNode& l = b->nodes[(size_t)left];
+  BNode& r = b->nodes[(size_t)right];
+  nd.m = l.m + r.m; nd.n = l.n + r.n;
+  int rc;
+  if ((rc = copy_block(nd.blk[BK_B12], B12, ldb12, l.kr, r.kw, "add_branch B12"))) return rc;
+  if ((rc = copy_block(nd.blk[BK_B21], B21, ldb21, r.kr, l.kw, "add_branch B21"))) return rc;
+  // translators of the children: R1 kr(left) x kr, W1 kw(left) x kw, ... (hssmatrix.jl:308-322)
+  if ((rc = copy_block(l.blk[BK_R], R1, ldr1, l.kr, kr, "add_branch R1"))) return rc;
+  if ((rc = copy_block(l.blk[BK_W], W1, ldw1, l.kw, kw, "add_branch W1"))) return rc;
+  if ((rc = copy_block(r.blk[BK_R], R2, ldr2, r.kr, kr, "add_branch R2"))) return rc;
+  if ((rc = copy_block(r.blk[BK_W], W2, ldw2, r.kw, kw, "add_branch W2"))) return rc;
+  l.used = r.used = true;
+  b->nodes.push_back(std::move(nd));
+  return (int64_t)b->nodes.size() - 1;
+}
+
+int hssb_builder_finalize(hssb_builder* b, int64_t root, int device, int shard_rank, int n_shards, hssb_matrix** out) {
+  if (!b || !out) HSSB_FAIL(HSSB_ERR_ARG, "finalize: NULL argument");
+  *out = nullptr;
+  if (root < 0 || root >= (int64_t)b->nodes.size()) HSSB_FAIL(HSSB_ERR_ARG, "finalize: invalid root id");
+  int rc = check_device(device);
+  if (rc) return rc;
+  std::unique_ptr<hssb_matrix> H(new (std::nothrow) hssb_matrix());
+  if (!H) HSSB_FAIL(HSSB_ERR_ALLOC, "finalize: out of memory");
+  H->device = device; H->shard_rank = shard_rank; H->n_shards = n_shards;
+  std::vector<BlockSource> src;
+  nodes_from_builder(b, root, H.get(), src);
+  rc = finish_matrix(H.get(), &src);
+  if (rc) { hssb_destroy(H.release()); return rc; }
+  *out = H.release();
+  return HSSB_OK;
+}
+
+int hssb_create_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, int device, int shard_rank,
+                          int n_shards, hssb_matrix** out) {
+  if (!out) HSSB_FAIL(HSSB_ERR_ARG, "create_synthetic: out is NULL");
+  *out = nullptr;
+  if (n <= 0 || leafsize <= 0 || rank < 0 || rank > INT32_MAX) HSSB_FAIL(HSSB_ERR_ARG, "create_synthetic: bad sizes");
+  if (!is_pow2(n_shards)) HSSB_FAIL(HSSB_ERR_ARG, "n_shards must be a power of two");
+  int rc = check_device(device);
+  if (rc) return rc;
+  std::unique_ptr<hssb_matrix> H(new (std::nothrow) hssb_matrix());
+  if (!H) HSSB_FAIL(HSSB_ERR_ALLOC, "create_synthetic: out of memory");
+  H->device = device; H->shard_rank = shard_rank; H->n_shards = n_shards;
+  H->synthetic = true; H->seed = seed;
+  nodes_synthetic(H.get(), n, leafsize, rank);
+  H->synth_rank = rank;  // translator scale 1/sqrt(2 rank)
+  rc = finish_matrix(H.get(), nullptr);
+  if (rc) { hssb_destroy(H.release()); return rc; }
+  *out = H.release();
+  return HSSB_OK;
+}
+
+int hssb_synthetic_rhs(uint64_t seed, int64_t n, int64_t nrhs, int64_t row0, int64_t rows, double* dX, int64_t ldx,
+                       int device, void* stream) {
+  if (!dX || n <= 0 || nrhs < 0 || rows < 0 || row0 < 0 || row0 + rows > n || ldx < rows)
+    HSSB_FAIL(HSSB_ERR_ARG, "synthetic_rhs: bad arguments");
+  int rc = check_device(device);
+  if (rc) return rc;
+  DeviceGuard dg(device);
+  if (rows * nrhs == 0) return HSSB_OK;
+  const int64_t total = rows * nrhs;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, 148 * 32);
+  synth_rhs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(synth_key(seed, 0, KIND_X), n, nrhs, row0, rows, dX, ldx);
+  HSSB_CUDA(cudaGetLastError());
+  return HSSB_OK;
+}
+
+int hssb_destroy(hssb_matrix* h) {
+  if (!h) return HSSB_OK;
+  if (h->device < 0) { delete h; return HSSB_OK; }
+  DeviceGuard dg(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
+  invalidate_graphs(h);
+  free_fast(h);
+  for (auto e : h->prof_events) cudaEventDestroy(e);
+  if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+  cudaFree(h->pool_dev);
+  cudaFree(h->tasks_dev);
+  cudaFree(h->z_dev);
+  cudaFree(h->f_dev);
+  cudaFree(h->x_stage);
+  cudaFree(h->y_stage);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  cudaGetLastError();
+  delete h;
+  return HSSB_OK;
+}
+
+int hssb_info(const hssb_matrix* h, hssb_info_t* o) {
+  if (!h || !o) HSSB_FAIL(HSSB_ERR_ARG, "hssb_info: NULL argument");
+  memset(o, 0, sizeof(*o));
+  o->m = h->m; o->n = h->n; o->local_m = h->local_m; o->local_n = h->local_n;
+  o->local_row0 = h->local_row0; o->local_col0 = h->local_col0;
+  o->n_nodes = (int64_t)h->nodes.size(); o->n_leaves = (int64_t)h->leaves.size(); o->depth = h->depth;
+  o->max_leaf_m = h->max_leaf_m; o->max_leaf_n = h->max_leaf_n; o->max_rank = h->max_rank;
+  o->pool_bytes = h->pool_len * 8; o->gen_elems = h->gen_elems; o->flops_per_rhs = h->flops_per_rhs;
+  o->z_rows = h->z_rows; o->f_rows = h->f_rows;
+  o->shard_rank = h->shard_rank; o->n_shards = h->n_shards; o->device = h->device;
+  o->uniform = h->uniform ? 1 : 0;
+  return HSSB_OK;
+}
+
+int hssb_node_info(const hssb_matrix* h, int64_t node, hssb_node_t* o) {
+  if (!h || !o) HSSB_FAIL(HSSB_ERR_ARG, "hssb_node_info: NULL argument");
+  if (node < 0 || node >= (int64_t)h->nodes.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_node_info: node id out of range");
+  const Node& t = h->nodes[(size_t)node];
+  o->left = t.left; o->right = t.right; o->parent = t.parent;
+  o->depth = t.depth; o->is_leaf = t.leaf; o->is_remote = t.remote;
+  o->row0 = t.row0; o->m = t.m; o->col0 = t.col0; o->n = t.n; o->kr = t.kr; o->kw = t.kw;
+  return HSSB_OK;
+}
+
+int hssb_get_block(const hssb_matrix* h, int64_t node, int kind, double* out, int64_t out_len) {
+  if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_get_block: NULL handle");
+  if (node < 0 || node >= (int64_t)h->nodes.size() || kind < 0 || kind >= BK_COUNT)
+    HSSB_FAIL(HSSB_ERR_ARG, "hssb_get_block: bad node or kind");
+  const Node& t = h->nodes[(size_t)node];
+  const int64_t rows = t.rows[kind], cols = t.cols[kind];
+  if (out_len < rows * cols) HSSB_FAIL(HSSB_ERR_ARG, "hssb_get_block: need %lld doubles", (long long)(rows * cols));
+  if (rows * cols == 0 || t.off[kind] < 0) return HSSB_OK;
+  if (!out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_get_block: out is NULL");
+  if (h->device < 0) {
+    for (int64_t j = 0; j < cols; ++j)
+      memcpy(out + j * rows, h->pool_host.data() + t.off[kind] + j * t.ld[kind], (size_t)rows * 8);
+    return HSSB_OK;
+  }
+  DeviceGuard dg(h->device);
+  HSSB_CUDA(cudaMemcpy2D(out, (size_t)rows * 8, h->pool_dev + t.off[kind], (size_t)t.ld[kind] * 8, (size_t)rows * 8,
+                         (size_t)cols, cudaMemcpyDeviceToHost));
+  return HSSB_OK;
+}
+
+int hssb_reserve(hssb_matrix* h, int64_t max_nrhs) {
+  if (!h || max_nrhs < 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_reserve: bad argument");
+  if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle has no device");
+  DeviceGuard dg(h->device);
+  return ensure_workspace(h, max_nrhs);
+}
+
+int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* dX, int64_t ldx,
+                    double* dY, int64_t ldy, double alpha, double beta, void* stream) {
+  if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
+  // DimensionMismatch checks of matmul.jl:19-20
+  if (rows_x != h->local_n)
+    HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: first dimension of B (%lld) does not match second dimension of A (%lld)",
+              (long long)rows_x, (long long)h->local_n);
+  if (rows_y != h->local_m)
+    HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: dimensions of C (%lld rows) don't match up with A (%lld rows)",
+              (long long)rows_y, (long long)h->local_m);
+  if (nrhs < 0 || nrhs > INT32_MAX) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: bad nrhs");
+  if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle: hssb200 has no CPU fallback, the product needs a B200");
+  if (nrhs == 0 || rows_y == 0) return HSSB_OK;
+  if (ldx < std::max<int64_t>(rows_x, 1) || ldy < rows_y) HSSB_FAIL(HSSB_ERR_DIM, "hssb_matmul: leading dimension too small");
+  if ((rows_x > 0 && !dX) || !dY) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL matrix pointer");
+  DeviceGuard dg(h->device);
+  if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
+  int rc = ensure_workspace(h, nrhs);
+  if (rc) return rc;
+  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  CallParams cp;
+  cp.pool = h->pool_dev; cp.X = dX; cp.Y = dY; cp.Z = h->z_dev; cp.F = h->f_dev;
+  cp.ldx = ldx; cp.ldy = ldy; cp.nrhs = (int32_t)nrhs; cp.alpha = alpha; cp.beta = beta;
+  if (h->use_graph && h->n_shards == 1) return run_graph(h, cp, st);
+  return run_phases(h, cp, st);
+}
+
+int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx, double* Y,
+                int64_t ldy, double alpha, double beta) {
+  if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
+  if (rows_x != h->local_n)
+    HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: first dimension of B (%lld) does not match second dimension of A (%lld)",
+              (long long)rows_x, (long long)h->local_n);
+  if (rows_y != h->local_m)
+    HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: dimensions of C (%lld rows) don't match up with A (%lld rows)",
+              (long long)rows_y, (long long)h->local_m);
+  if (nrhs < 0 || nrhs > INT32_MAX) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: bad nrhs");
+  if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle: hssb200 has no CPU fallback, the product needs a B200");
+  if (nrhs == 0 || rows_y == 0) return HSSB_OK;
+  if (ldx < std::max<int64_t>(rows_x, 1) || ldy < rows_y) HSSB_FAIL(HSSB_ERR_DIM, "hssb_matmul: leading dimension too small");
+  if ((rows_x > 0 && !X) || !Y) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL matrix pointer");
+  DeviceGuard dg(h->device);
+  if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
+  if (nrhs > h->stage_nrhs) {
+    cudaFree(h->x_stage); cudaFree(h->y_stage);
+    h->x_stage = h->y_stage = nullptr; h->stage_nrhs = 0;
+    const size_t xb = (size_t)std::max<int64_t>(h->local_n, 1) * (size_t)nrhs * 8, yb = (size_t)h->local_m * (size_t)nrhs * 8;
+    if (cudaMalloc(&h->x_stage, xb) != cudaSuccess || cudaMalloc(&h->y_stage, yb) != cudaSuccess) {
+      cudaGetLastError();
+      HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of X/Y staging (%.3f GB) failed", (xb + yb) * 1e-9);
+    }
+    h->stage_nrhs = nrhs;
+    invalidate_graphs(h);
+  }
+  const int64_t sx = std::max<int64_t>(h->local_n, 1), sy = h->local_m;
+  if (rows_x > 0)
+    HSSB_CUDA(cudaMemcpy2DAsync(h->x_stage, (size_t)sx * 8, X, (size_t)ldx * 8, (size_t)rows_x * 8, (size_t)nrhs,
+                                cudaMemcpyHostToDevice, h->stream));
+  if (beta != 0.0)
+    HSSB_CUDA(cudaMemcpy2DAsync(h->y_stage, (size_t)sy * 8, Y, (size_t)ldy * 8, (size_t)rows_y * 8, (size_t)nrhs,
+                                cudaMemcpyHostToDevice, h->stream));
+  int rc = hssb_matmul_dev(h, rows_y, rows_x, nrhs, h->x_stage, sx, h->y_stage, sy, alpha, beta, h->stream);
+  if (rc) return rc;
+  HSSB_CUDA(cudaMemcpy2DAsync(Y, (size_t)ldy * 8, h->y_stage, (size_t)sy * 8, (size_t)rows_y * 8, (size_t)nrhs,
+                              cudaMemcpyDeviceToHost, h->stream));
+  HSSB_CUDA(cudaStreamSynchronize(h->stream));
+  return HSSB_OK;
+}
+
+int hssb_sync(hssb_matrix* h) {
+  if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_sync: NULL handle");
+  if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle has no device");
+  DeviceGuard dg(h->device);
+  HSSB_CUDA(cudaStreamSynchronize(h->stream));
+  return HSSB_OK;
+}
+
+int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
+  if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_set_option: NULL handle");
+  switch (opt) {
+    case HSSB_OPT_FORCE_GENERIC: h->force_generic = value != 0; break;
+    case HSSB_OPT_USE_GRAPH: h->use_graph = value != 0; break;
+    case HSSB_OPT_FUSED_LEAF: h->fused_leaf = value != 0; break;
+    case HSSB_OPT_PROFILE: h->profile = value != 0; break;
+    default: HSSB_FAIL(HSSB_ERR_ARG, "hssb_set_option: unknown option %d", opt);
+  }
+  if (h->device < 0) return HSSB_OK;
+  DeviceGuard dg(h->device);
+  invalidate_graphs(h);
+  return HSSB_OK;
+}
+
+int64_t hssb_get_option(const hssb_matrix* h, int opt) {
+  if (!h) return -1;
+  switch (opt) {
+    case HSSB_OPT_FORCE_GENERIC: return h->force_generic;
+    case HSSB_OPT_USE_GRAPH: return h->use_graph;
+    case HSSB_OPT_FUSED_LEAF: return h->fused_leaf;
+    case HSSB_OPT_PROFILE: return h->profile;
+    default: return -1;
+  }
+}
+
+int64_t hssb_launch_count(const hssb_matrix* h) { return h ? h->launches : 0; }
+
+int hssb_phase_count(const hssb_matrix* h) { return h ? (int)h->phases.size() : 0; }
+
+int hssb_phase_time(hssb_matrix* h, int i, hssb_phase_time_t* o) {
+  if (!h || !o || i < 0 || i >= (int)h->phases.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_phase_time: bad argument");
+  const Phase& ph = h->phases[(size_t)i];
+  memset(o, 0, sizeof(*o));
+  o->kind = ph.kind; o->level = ph.level; o->top = ph.top; o->fast = ph.fast; o->ntasks = ph.ntasks;
+  int64_t gen = 0, xrows = 0, yrows = 0, fl = 0;
+  for (int64_t t = ph.task0; t < ph.task0 + ph.ntasks; ++t) {
+    const GTask& g = h->tasks_host[(size_t)t];
+    gen += (int64_t)g.M * g.K0 + (int64_t)g.M * g.K1;
+    fl += 2ll * g.M * ((int64_t)g.K0 + g.K1);
+    if (g.sb0 == SRC_X) xrows += g.K0;
+    if (g.sc == SRC_Y) yrows += g.M;
+  }
+  o->flops_per_rhs = fl; o->gen_elems = gen; o->x_rows = xrows; o->y_rows = yrows;
+  o->ms = -1.0;
+  if (h->device >= 0 && h->prof_events.size() > (size_t)i + 1 && h->prof_nrhs > 0) {
+    DeviceGuard dg(h->device);
+    HSSB_CUDA(cudaEventSynchronize(h->prof_events[(size_t)i + 1]));
+    float ms = 0;
+    HSSB_CUDA(cudaEventElapsedTime(&ms, h->prof_events[(size_t)i], h->prof_events[(size_t)i + 1]));
+    o->ms = ms;
+  }
+  return HSSB_OK;
+}
+
+int hssb_comm_unique_id(void* id128) {
+  if (!id128) HSSB_FAIL(HSSB_ERR_ARG, "hssb_comm_unique_id: NULL buffer");
+  int rc = load_nccl();
+  if (rc) return rc;
+  HSSB_NCCL(g_nccl.GetUniqueId(id128));
+  return HSSB_OK;
+}
+
+int hssb_comm_init(hssb_matrix* h, const void* id128, int rank, int n_ranks) {
+  if (!h || !id128) HSSB_FAIL(HSSB_ERR_ARG, "hssb_comm_init: NULL argument");
+  if (n_ranks != h->n_shards || rank != h->shard_rank)
+    HSSB_FAIL(HSSB_ERR_ARG, "hssb_comm_init: rank %d/%d does not match shard %d/%d", rank, n_ranks, h->shard_rank, h->n_shards);
+  int rc = load_nccl();
+  if (rc) return rc;
+  DeviceGuard dg(h->device);
+  Id128 id;
+  memcpy(id.b, id128, 128);
+  void* comm = nullptr;
+  HSSB_NCCL(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
+  h->nccl_comm = comm;
+  return HSSB_OK;
+}
+
+
+// ---- test hooks: host-only planning (no device required) --------------------
+int hssb_plan_only(hssb_builder* b, int64_t root, int shard_rank, int n_shards, hssb_matrix** out) {
+  if (!b || !out) HSSB_FAIL(HSSB_ERR_ARG, "plan_only: NULL argument");
+  *out = nullptr;
+  if (root < 0 || root >= (int64_t)b->nodes.size()) HSSB_FAIL(HSSB_ERR_ARG, "plan_only: invalid root id");
+  std::unique_ptr<hssb_matrix> H(new (std::nothrow) hssb_matrix());
+  if (!H) HSSB_FAIL(HSSB_ERR_ALLOC, "plan_only: out of memory");
+  H->device = -1; H->shard_rank = shard_rank; H->n_shards = n_shards;
+  std::vector<BlockSource> src;
+  nodes_from_builder(b, root, H.get(), src);
+  int rc = plan_matrix(H.get());
+  if (rc) return rc;
+  fill_pool_host(H.get(), &src);
+  *out = H.release();
+  return HSSB_OK;
+}
+
+int hssb_plan_only_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, int shard_rank, int n_shards,
+                             hssb_matrix** out) {
+  if (!out) HSSB_FAIL(HSSB_ERR_ARG, "plan_only_synthetic: out is NULL");
+  *out = nullptr;
+  if (n <= 0 || leafsize <= 0 || rank < 0) HSSB_FAIL(HSSB_ERR_ARG, "plan_only_synthetic: bad sizes");
+  if (!is_pow2(n_shards)) HSSB_FAIL(HSSB_ERR_ARG, "n_shards must be a power of two");
+  std::unique_ptr<hssb_matrix> H(new (std::nothrow) hssb_matrix());
+  if (!H) HSSB_FAIL(HSSB_ERR_ALLOC, "plan_only_synthetic: out of memory");
+  H->device = -1; H->shard_rank = shard_rank; H->n_shards = n_shards;
+  H->synthetic = true; H->seed = seed; H->synth_rank = rank;
+  nodes_synthetic(H.get(), n, leafsize, rank);
+  int rc = plan_matrix(H.get());
+  if (rc) return rc;
+  fill_pool_host(H.get(), nullptr);
+  *out = H.release();
+  return HSSB_OK;
+}
+
+int hssb_debug_counts(const hssb_matrix* h, int64_t* n_tasks, int64_t* n_phases, int64_t* pool_len) {
+  if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_counts: NULL handle");
+  if (n_tasks) *n_tasks = (int64_t)h->tasks_host.size();
+  if (n_phases) *n_phases = (int64_t)h->phases.size();
+  if (pool_len) *pool_len = h->pool_len;
+  return HSSB_OK;
+}
+
+int hssb_debug_task(const hssb_matrix* h, int64_t i, hssb_task_t* o) {
+  if (!h || !o || i < 0 || i >= (int64_t)h->tasks_host.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_task: bad argument");
+  const GTask& t = h->tasks_host[(size_t)i];
+  o->a0 = t.a0; o->a1 = t.a1; o->b0 = t.b0; o->b1 = t.b1; o->c = t.c;
+  o->lda0 = t.lda0; o->lda1 = t.lda1; o->ldb0 = t.ldb0; o->ldb1 = t.ldb1; o->ldc = t.ldc;
+  o->M = t.M; o->K0 = t.K0; o->K1 = t.K1; o->ta0 = t.ta0; o->ta1 = t.ta1;
+  o->sb0 = t.sb0; o->sb1 = t.sb1; o->sc = t.sc; o->epilogue = t.epilogue;
+  return HSSB_OK;
+}
+
+int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* o) {
+  if (!h || !o || i < 0 || i >= (int64_t)h->phases.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_phase: bad argument");
+  const Phase& p = h->phases[(size_t)i];
+  o->kind = p.kind; o->task0 = p.task0; o->ntasks = p.ntasks; o->maxM = p.maxM; o->level = p.level;
+  o->top = p.top; o->fast = p.fast;
+  o->xchg_zoff = h->xchg_zoff; o->xchg_slot_rows = h->xchg_slot_rows;
+  return HSSB_OK;
+}
+
+int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len) {
+  if (!h || !out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_pool: NULL argument");
+  if (len < h->pool_len) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_pool: need %lld doubles", (long long)h->pool_len);
+  if (!h->pool_host.empty()) { memcpy(out, h->pool_host.data(), (size_t)h->pool_len * 8); return HSSB_OK; }
+  if (h->device < 0 || !h->pool_dev) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_pool: no pool image");
+  DeviceGuard dg(h->device);
+  HSSB_CUDA(cudaMemcpy(out, h->pool_dev, (size_t)h->pool_len * 8, cudaMemcpyDeviceToHost));
+  return HSSB_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,122 @@
+// hssb_diag.cu — measurement helpers behind hssb_measure_peak (bench.py's
+// roofline denominators).  MEASURED_PEAKS.json carries HBM and bf16 numbers but
+// no FP64 figure, and this path is FP64: the DFMA / DMMA peaks are measured live
+// with register-resident loops, the copy bandwidth with a plain 16-byte copy.
+#include <cuda_runtime.h>
+
+#include "hssb_internal.h"
+#include "hssb_mma.cuh"
+
+namespace hssb {
+
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters, double seed) {
+  double a[8], x = seed + threadIdx.x * 1e-9, y = 1.0 - 1e-9;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) a[i] = seed * (i + 1);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = fma(a[i], y, x);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += a[i];
+  if (s == 123.456) out[0] = s;  // never true; keeps the loop alive
+}
+
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double seed) {
+  double c[8][2];
+  const double a = seed + threadIdx.x * 1e-9, b = 1e-3 * seed;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) mma_m8n8k4(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
+__global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+
+}  // namespace hssb
+
+using namespace hssb;
+
+extern "C" int hssb_measure_peak(int device, int kind, int64_t arg, double* out) {
+  if (!out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_measure_peak: out is NULL");
+  *out = 0.0;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+    cudaGetLastError();
+    HSSB_FAIL(HSSB_ERR_CUDA, "hssb_measure_peak: no usable CUDA device");
+  }
+  int prev = 0;
+  cudaGetDevice(&prev);
+  HSSB_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  HSSB_CUDA(cudaGetDeviceProperties(&prop, device));
+  cudaEvent_t e0, e1;
+  HSSB_CUDA(cudaEventCreate(&e0));
+  HSSB_CUDA(cudaEventCreate(&e1));
+  double best = 0.0;
+  int rc = HSSB_OK;
+  if (kind == 0 || kind == 1) {
+    const int iters = arg > 0 ? (int)arg : 20000;
+    const int grid = prop.multiProcessorCount * 4;
+    double* d = nullptr;
+    HSSB_CUDA(cudaMalloc(&d, 64));
+    for (int rep = 0; rep < 4; ++rep) {
+      HSSB_CUDA(cudaEventRecord(e0));
+      if (kind == 0) dfma_peak_kernel<<<grid, 256>>>(d, iters, 0.5);
+      else dmma_peak_kernel<<<grid, 256>>>(d, iters, 0.5);
+      HSSB_CUDA(cudaEventRecord(e1));
+      HSSB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      HSSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      // DFMA: 8 FMAs/thread/iter; DMMA: 8 m8n8k4 (= 512 flops) per warp per iter
+      const double flops = kind == 0 ? 2.0 * 8 * iters * 256.0 * grid : 8.0 * 512.0 * iters * 8.0 * grid;
+      if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaFree(d);
+  } else if (kind == 2) {
+    const int64_t bytes = arg > 0 ? arg : ((int64_t)1 << 30);
+    const int64_t n2 = bytes / 16;
+    double2 *a = nullptr, *b = nullptr;
+    if (cudaMalloc(&a, (size_t)n2 * 16) != cudaSuccess || cudaMalloc(&b, (size_t)n2 * 16) != cudaSuccess) {
+      cudaGetLastError();
+      cudaFree(a);
+      set_error("hssb_measure_peak: allocation failed");
+      rc = HSSB_ERR_ALLOC;
+    } else {
+      cudaMemset(a, 0, (size_t)n2 * 16);
+      for (int rep = 0; rep < 6; ++rep) {
+        cudaEventRecord(e0);
+        copy_kernel<<<prop.multiProcessorCount * 16, 256>>>(a, b, n2);
+        cudaEventRecord(e1);
+        cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0) best = std::max(best, 2.0 * n2 * 16.0 / (ms * 1e-3) * 1e-9);
+      }
+      cudaFree(a);
+      cudaFree(b);
+    }
+  } else {
+    set_error("hssb_measure_peak: unknown kind %d", kind);
+    rc = HSSB_ERR_ARG;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaSetDevice(prev);
+  if (cudaGetLastError() != cudaSuccess && rc == HSSB_OK) {
+    set_error("hssb_measure_peak: CUDA failure");
+    rc = HSSB_ERR_CUDA;
+  }
+  *out = best;
+  return rc;
+}

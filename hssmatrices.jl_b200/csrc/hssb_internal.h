@@ -1,0 +1,150 @@
+// hssb_internal.h — shared host/device declarations of the hssb200 library.
+// Not part of the public ABI (that is include/hssb200.h).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/hssb200.h"
+
+namespace hssb {
+
+// ---------------------------------------------------------------- errors ---
+void set_error(const char* fmt, ...);
+#define HSSB_FAIL(code, ...)      \
+  do {                            \
+    ::hssb::set_error(__VA_ARGS__); \
+    return (code);                \
+  } while (0)
+#define HSSB_CUDA(expr)                                                              \
+  do {                                                                               \
+    cudaError_t _e = (expr);                                                         \
+    if (_e != cudaSuccess) {                                                         \
+      ::hssb::set_error("CUDA error %s at %s:%d: %s", cudaGetErrorName(_e), __FILE__, \
+                        __LINE__, cudaGetErrorString(_e));                           \
+      return HSSB_ERR_CUDA;                                                          \
+    }                                                                                \
+  } while (0)
+
+// ------------------------------------------------- block kinds / sources ---
+enum BlockKind : int { BK_D = 0, BK_U, BK_V, BK_B12, BK_B21, BK_R, BK_W, BK_COUNT };
+enum OperandSrc : int { SRC_X = 0, SRC_Z = 1, SRC_F = 2, SRC_Y = 3 };
+
+// One task of the generic (any-shape) kernel:
+//   C[M x N] = alpha * (op(A0)[M x K0] * B0[K0 x N] + op(A1)[M x K1] * B1[K1 x N]) + beta * C
+// A0/A1 live in the generator pool; B0/B1/C are the user's X / Y or a block of the
+// Z / F workspace.  Every step of src/matmul.jl:32-62 has this form:
+//   leaf up    Z = V' X                     (matmul.jl:34)
+//   merge      Z = W1' Z1 + W2' Z2          (matmul.jl:39)
+//   translate  F1 = B12 Z2 + R1 F           (matmul.jl:52-56)
+//   leaf down  Y = a (D X + U F) + b Y      (matmul.jl:46-47)
+struct GTask {
+  int64_t a0, a1;     // pool offsets (doubles)
+  int64_t b0, b1, c;  // X/Y: first row; Z/F: workspace row offset (element offset = row * nrhs)
+  int32_t lda0, lda1;
+  int32_t ldb0, ldb1, ldc;  // leading dimensions of workspace operands (ignored for X/Y)
+  int32_t M, K0, K1;
+  uint8_t ta0, ta1;         // 1: op(A) = A'
+  uint8_t sb0, sb1, sc;     // OperandSrc
+  uint8_t epilogue;         // 1: C = alpha*acc + beta*C, 0: C = acc
+  uint8_t pad[2];
+};
+
+struct CallParams {
+  const double* pool;
+  const double* X;
+  double* Y;
+  double* Z;
+  double* F;
+  int64_t ldx, ldy;
+  int32_t nrhs;
+  double alpha, beta;
+};
+
+// ------------------------------------------------------------- host tree ---
+struct HostBlock {  // where a generator block comes from
+  std::vector<double> data;  // compact copy, ld = rows (empty for synthetic / absent blocks)
+  int64_t rows = 0, cols = 0;
+};
+
+struct Node {
+  int64_t left = -1, right = -1, parent = -1;
+  int32_t depth = 0, height = 0;
+  bool leaf = false, remote = false, top = false;  // top: above the shard cut (replicated)
+  bool local = true;                               // inside this shard's subtree
+  int64_t row0 = 0, col0 = 0, m = 0, n = 0;
+  int64_t kr = 0, kw = 0;        // gensize (hssmatrix.jl:254-262); 0 at the root
+  uint64_t heap_id = 1;          // synthetic generator stream id
+  // packed generator blocks (pool offsets in doubles, -1 = absent)
+  int64_t off[BK_COUNT] = {-1, -1, -1, -1, -1, -1, -1};
+  int32_t ld[BK_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  int64_t rows[BK_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  int64_t cols[BK_COUNT] = {0, 0, 0, 0, 0, 0, 0};
+  int64_t zoff = -1, foff = -1;  // workspace row offsets
+  int32_t ldz = 0, ldf = 0;
+};
+
+enum PhaseKind : int { PH_LEAF_UP = 0, PH_MERGE, PH_EXCHANGE, PH_TRANSLATE, PH_LEAF_DOWN };
+
+struct Phase {
+  int kind;
+  int64_t task0 = 0, ntasks = 0;  // range in the task array
+  int32_t maxM = 0;
+  int32_t level = 0;              // height (merge) or depth (translate)
+  bool top = false;               // replicated top-tree phase
+  int fast = 0;                   // fixed-shape kernel id (0 = generic)
+};
+
+}  // namespace hssb
+
+// The opaque handle of the public ABI.
+struct hssb_matrix {
+  int device = 0;
+  int shard_rank = 0, n_shards = 1;
+  std::vector<hssb::Node> nodes;  // BFS order, root = 0
+  std::vector<int64_t> leaves;    // local leaves, left to right
+  std::vector<hssb::Phase> phases;
+  std::vector<hssb::GTask> tasks_host;
+  hssb::GTask* tasks_dev = nullptr;
+  double* pool_dev = nullptr;
+  std::vector<double> pool_host;  // plan-only handles (CPU tests): host image of the pool
+  int64_t pool_len = 0;  // doubles
+  int64_t gen_elems = 0, flops_per_rhs = 0;
+  int64_t z_rows = 0, f_rows = 0;
+  int64_t ws_nrhs = 0;  // workspace capacity in columns
+  double* z_dev = nullptr;
+  double* f_dev = nullptr;
+  // staging for the host-pointer entry
+  double* x_stage = nullptr;
+  double* y_stage = nullptr;
+  int64_t stage_nrhs = 0;
+  cudaStream_t stream = nullptr;
+  int64_t launches = 0;
+  // global / local shape
+  int64_t m = 0, n = 0, local_m = 0, local_n = 0, local_row0 = 0, local_col0 = 0;
+  int64_t depth = 0, max_leaf_m = 0, max_leaf_n = 0, max_rank = 0;
+  bool uniform = false;
+  int64_t uni_m = 0, uni_r = 0;  // leaf size / rank when uniform
+  // exchange
+  int64_t xchg_zoff = -1, xchg_slot_rows = 0;  // all-gather buffer = P slots of slot_rows x nrhs
+  void* nccl_comm = nullptr;
+  // options
+  bool force_generic = false, use_graph = false, fused_leaf = false, profile = false;
+  std::vector<cudaEvent_t> prof_events;  // HSSB_OPT_PROFILE: one event between consecutive phases
+  int64_t prof_nrhs = 0;
+  // synthetic
+  bool synthetic = false;
+  uint64_t seed = 0;
+  int64_t synth_rank = 0;
+  // CUDA-graph cache (HSSB_OPT_USE_GRAPH): one instantiated graph per distinct call signature
+  struct GraphSlot {
+    hssb::CallParams cp;
+    cudaGraphExec_t exec = nullptr;
+    int64_t kernels = 0;
+  };
+  std::vector<GraphSlot> graphs;
+  // fixed-shape kernel state (hssb_fast.cuh)
+  void* fast_state = nullptr;
+};

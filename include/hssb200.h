@@ -1,0 +1,218 @@
+/* hssb200.h — C ABI of the B200-native HSS x dense product.
+ *
+ * Drop-in boundary for ONE path of bonevbs/HssMatrices.jl (v0.1.6):
+ *     *(hssA::HssMatrix, B::AbstractMatrix)            src/matmul.jl:13
+ *     *(hssA::HssMatrix, x::AbstractVector)            src/matmul.jl:15
+ *     mul!(C, hssA::HssMatrix, B, alpha, beta)         src/matmul.jl:18-28
+ *       _matmatup   (post-order upsweep)               src/matmul.jl:32-42
+ *       _matmatdown! (pre-order downsweep)             src/matmul.jl:44-62
+ * The reference has no FFI for this path (it is pure Julia on OpenBLAS), so the
+ * entry points below are what a Julia `ccall` binding for it needs; the binding
+ * itself is hssmatrices.jl_b200/julia/HssMatricesB200.jl and is walked through
+ * in INTEGRATION.md.
+ *
+ * Conventions: extern "C"; plain pointers and sizes; all matrices Float64,
+ * column-major with an explicit leading dimension (Julia `stride(A,2)`); every
+ * function returns 0 on success or a negative hssb_status and never throws;
+ * hssb_last_error() returns a thread-local message for the last failure.
+ * There is NO CPU fallback: every compute entry point fails with
+ * HSSB_ERR_CUDA when no sm_100 device is usable.
+ */
+#ifndef HSSB200_H
+#define HSSB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HSSB_VERSION 100 /* 0.1.0 */
+
+typedef enum hssb_status {
+  HSSB_OK = 0,
+  HSSB_ERR_ARG = -1,      /* bad pointer / size / id                                   */
+  HSSB_ERR_DIM = -2,      /* Julia DimensionMismatch: matmul.jl:19-20, hssmatrix.jl:41-42,58-59 */
+  HSSB_ERR_CUDA = -3,     /* CUDA runtime error or no usable device                    */
+  HSSB_ERR_ALLOC = -4,    /* host or device allocation failed                          */
+  HSSB_ERR_STATE = -5,    /* call not valid in this state (e.g. comm not initialised)  */
+  HSSB_ERR_COMM = -6      /* NCCL error / NCCL not loadable                            */
+} hssb_status;
+
+typedef struct hssb_builder hssb_builder; /* host-side packer front end */
+typedef struct hssb_matrix hssb_matrix;   /* packed, device-resident HSS matrix */
+
+/* ---- library ---------------------------------------------------------- */
+int hssb_version(void);
+const char* hssb_last_error(void);
+/* Number of CUDA devices with compute capability 10.x (0 if none / no driver). */
+int hssb_device_count(void);
+
+/* ---- packer: flattens the recursive HssMatrix (src/hssmatrix.jl:11-68) --- */
+/* The caller walks its tree in post-order and registers every node; block data
+ * is copied out during the call, so Julia only needs GC.@preserve per call.
+ * Node ids are returned (>= 0) or a negative hssb_status.                   */
+int hssb_builder_create(hssb_builder** out);
+void hssb_builder_destroy(hssb_builder* b);
+
+/* Leaf node: HssMatrix(D, U, V) (hssmatrix.jl:40-44).  D is m x n, U is m x kr,
+ * V is n x kw; kr/kw may be 0 (then U/V may be NULL), as for HssMatrix(D)
+ * (hssmatrix.jl:36-39) and hss_blkdiag (compression.jl:447-475).             */
+int64_t hssb_builder_add_leaf(hssb_builder* b, int64_t m, int64_t n, int64_t kr, int64_t kw,
+                              const double* D, int64_t ldd, const double* U, int64_t ldu,
+                              const double* V, int64_t ldv);
+
+/* Branch node: HssMatrix(A11, A22, B12, B21, R1, W1, R2, W2) (hssmatrix.jl:56-67).
+ * B12 is kr(left) x kw(right), B21 is kr(right) x kw(left); R1/R2 are
+ * kr(child) x kr, W1/W2 are kw(child) x kw where (kr, kw) = gensize of this
+ * node (hssmatrix.jl:254-262).  For a root-style node (hssmatrix.jl:46-55) pass
+ * kr = kw = 0 and NULL translators.  Dimension violations return HSSB_ERR_DIM
+ * (the checks of hssmatrix.jl:308-322).                                      */
+int64_t hssb_builder_add_branch(hssb_builder* b, int64_t left, int64_t right, int64_t kr, int64_t kw,
+                                const double* B12, int64_t ldb12, const double* B21, int64_t ldb21,
+                                const double* R1, int64_t ldr1, const double* W1, int64_t ldw1,
+                                const double* R2, int64_t ldr2, const double* W2, int64_t ldw2);
+
+/* Placeholder for a subtree whose generators live on another GPU (multi-GPU
+ * subtree sharding): only its size and gensize are known here. */
+int64_t hssb_builder_add_remote(hssb_builder* b, int64_t m, int64_t n, int64_t kr, int64_t kw);
+
+/* Pack the tree under `root` into level-ordered device arrays on `device`.
+ * The node is treated as root exactly like rooted() (hssmatrix.jl:266; used at
+ * matmul.jl:24): its own R/W are ignored.  `shard_rank`/`n_shards` describe
+ * subtree sharding: with n_shards == 1 the tree must contain no remote nodes;
+ * with n_shards = P > 1 the tree must contain exactly P-1 remote placeholders
+ * and the local subtree must be the shard_rank-th of the P subtrees (left to
+ * right).  The builder can be destroyed afterwards.                          */
+int hssb_builder_finalize(hssb_builder* b, int64_t root, int device, int shard_rank, int n_shards,
+                          hssb_matrix** out);
+
+/* Synthetic random-generator HSS matrix generated ON THE DEVICE (BASELINE.json
+ * configs 3-5): bisection tree (clustertree.jl:27-35) on n with `leafsize`,
+ * every rank = `rank`, counter-based generator specified in
+ * oracle/hss_oracle.py (synth_*), bit-identical to that host twin.  With
+ * n_shards = P > 1 only the shard_rank-th depth-log2(P) subtree plus the
+ * replicated top tree is generated.                                          */
+int hssb_create_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, int device,
+                          int shard_rank, int n_shards, hssb_matrix** out);
+/* Fill rows [row0, row0+rows) of the n x nrhs synthetic right-hand side into
+ * device memory dX (leading dimension ldx).                                   */
+int hssb_synthetic_rhs(uint64_t seed, int64_t n, int64_t nrhs, int64_t row0, int64_t rows,
+                       double* dX, int64_t ldx, int device, void* stream);
+
+int hssb_destroy(hssb_matrix* h);
+
+/* ---- queries ---------------------------------------------------------- */
+typedef struct hssb_info_t {
+  int64_t m, n;                 /* global size(hssA) (hssmatrix.jl:94)                   */
+  int64_t local_m, local_n;     /* rows of Y / X owned by this shard                     */
+  int64_t local_row0, local_col0;
+  int64_t n_nodes, n_leaves, depth;
+  int64_t max_leaf_m, max_leaf_n, max_rank;
+  int64_t pool_bytes;           /* device bytes of packed generators (incl. padding)     */
+  int64_t gen_elems;            /* local generator doubles, unpadded (algorithmic)       */
+  int64_t flops_per_rhs;        /* local algorithmic flops per right-hand-side column    */
+  int64_t z_rows, f_rows;       /* workspace rows (x nrhs x 8 bytes each)                */
+  int32_t shard_rank, n_shards;
+  int32_t device;
+  int32_t uniform;              /* 1 if the fast fixed-shape kernels apply               */
+} hssb_info_t;
+int hssb_info(const hssb_matrix* h, hssb_info_t* out);
+
+/* Read back one generator block (test/debug): kind 0..6 = D,U,V,B12,B21,R,W of
+ * node `node` (ids in BFS order; see hssb_node_info).  out is rows x cols,
+ * column-major, ld = rows.                                                    */
+typedef struct hssb_node_t {
+  int64_t left, right, parent;  /* -1 if none */
+  int64_t depth, is_leaf, is_remote;
+  int64_t row0, m, col0, n, kr, kw;
+} hssb_node_t;
+int hssb_node_info(const hssb_matrix* h, int64_t node, hssb_node_t* out);
+int hssb_get_block(const hssb_matrix* h, int64_t node, int kind, double* out, int64_t out_len);
+
+/* ---- the product ------------------------------------------------------ */
+/* Pre-size the Z/F workspaces for up to max_nrhs columns (otherwise grown on
+ * demand inside the first call).                                             */
+int hssb_reserve(hssb_matrix* h, int64_t max_nrhs);
+
+/* mul!(C, hssA, B, alpha, beta) with HOST pointers (matmul.jl:18): copies the
+ * local rows of X to the device, runs the product, copies Y back, synchronous.
+ * beta == 0 never reads Y (matmul.jl:13 passes uninitialised memory).
+ * HSSB_ERR_DIM mirrors the DimensionMismatch of matmul.jl:19-20: rows_x must be
+ * local_n and rows_y local_m.                                                */
+int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
+                const double* X, int64_t ldx, double* Y, int64_t ldy, double alpha, double beta);
+
+/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t, NULL =
+ * the library's own stream).  This is the timed entry.                       */
+int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
+                    const double* dX, int64_t ldx, double* dY, int64_t ldy, double alpha, double beta,
+                    void* stream);
+int hssb_sync(hssb_matrix* h);
+
+/* Options. */
+#define HSSB_OPT_FORCE_GENERIC 1 /* 1: never use the fixed-shape DMMA kernels (debug/parity)  */
+#define HSSB_OPT_USE_GRAPH 2     /* 1: replay the level schedule as a CUDA graph              */
+#define HSSB_OPT_FUSED_LEAF 3    /* 1: form D*X in the upsweep leaf kernel (north-star variant) */
+#define HSSB_OPT_PROFILE 4       /* 1: record a CUDA event between phases (hssb_phase_time)   */
+int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
+int64_t hssb_get_option(const hssb_matrix* h, int opt);
+/* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
+int64_t hssb_launch_count(const hssb_matrix* h);
+
+/* Per-phase accounting of the level schedule and, after a call made with
+ * HSSB_OPT_PROFILE = 1 (graph replay off), its device time measured with CUDA
+ * events on the launching stream.  kind: 0 leaf-up, 1 merge, 2 exchange,
+ * 3 translate, 4 leaf-down.  ms < 0 if no profiled call was made.             */
+typedef struct hssb_phase_time_t {
+  int64_t kind, level, top, fast, ntasks;
+  int64_t flops_per_rhs; /* algorithmic flops per right-hand-side column        */
+  int64_t gen_elems;     /* generator doubles the phase reads                   */
+  int64_t x_rows, y_rows; /* rows of X read / rows of Y written (x nrhs x 8 B)  */
+  double ms;
+} hssb_phase_time_t;
+int hssb_phase_count(const hssb_matrix* h);
+int hssb_phase_time(hssb_matrix* h, int i, hssb_phase_time_t* out);
+
+/* ---- multi-GPU exchange (one rank per GPU) ---------------------------- */
+/* Rank 0 calls hssb_comm_unique_id and ships the 128 bytes to every rank by
+ * any means (torch.distributed broadcast, MPI, a file); every rank then calls
+ * hssb_comm_init.  The only collective on the path is one all-gather of the
+ * subtree-root Z blocks per product.                                         */
+int hssb_comm_unique_id(void* id128);
+int hssb_comm_init(hssb_matrix* h, const void* id128, int rank, int n_ranks);
+
+/* ---- measurement helpers (used by bench.py; not on the product path) --- */
+/* kind 0: FP64 FMA (DFMA) register-resident peak, kind 1: FP64 tensor (DMMA
+ * m8n8k4) peak, returns TFLOP/s.  kind 2: device copy bandwidth over `bytes`
+ * bytes (read+write counted), returns GB/s.                                  */
+int hssb_measure_peak(int device, int kind, int64_t bytes_or_iters, double* out);
+
+/* ---- test hooks: host-only planning (no device needed) ----------------- */
+/* Run the packer and the level scheduler without touching a GPU and expose the
+ * resulting task table, so that CPU-only tests can check pool layout, task
+ * wiring and shard plans with a numpy interpreter.  A plan-only handle cannot
+ * multiply: hssb_matmul* fail with HSSB_ERR_CUDA (there is no CPU fallback). */
+typedef struct hssb_task_t {
+  int64_t a0, a1, b0, b1, c;
+  int64_t lda0, lda1, ldb0, ldb1, ldc;
+  int64_t M, K0, K1;
+  int64_t ta0, ta1, sb0, sb1, sc, epilogue; /* sb/sc: 0 = X, 1 = Z, 2 = F, 3 = Y */
+} hssb_task_t;
+typedef struct hssb_phase_t {
+  int64_t kind; /* 0 leaf-up, 1 merge, 2 exchange, 3 translate, 4 leaf-down */
+  int64_t task0, ntasks, maxM, level, top, fast;
+  int64_t xchg_zoff, xchg_slot_rows;
+} hssb_phase_t;
+int hssb_plan_only(hssb_builder* b, int64_t root, int shard_rank, int n_shards, hssb_matrix** out);
+int hssb_plan_only_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, int shard_rank,
+                             int n_shards, hssb_matrix** out);
+int hssb_debug_counts(const hssb_matrix* h, int64_t* n_tasks, int64_t* n_phases, int64_t* pool_len);
+int hssb_debug_task(const hssb_matrix* h, int64_t i, hssb_task_t* out);
+int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* out);
+int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HSSB200_H */

@@ -1,0 +1,30 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def hb():
+    """The product package (hssmatrices.jl_b200 via the hssb200 shim), with the library built."""
+    import hssb200
+    if not os.path.exists(hssb200.LIB_PATH):
+        import __graft_entry__ as g
+        g.build()
+    hssb200.lib()
+    return hssb200
+
+
+@pytest.fixture(scope="session")
+def oracle():
+    import hss_oracle
+    return hss_oracle

@@ -1,0 +1,43 @@
+"""torchrun worker: one rank per GPU, subtree-sharded synthetic matrix, one
+NCCL all-gather per product; compares the gathered result with the oracle."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
+import hssb200 as hb  # noqa: E402
+import hss_oracle as o  # noqa: E402
+
+
+def main():
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
+    n, ls, r, k, seed = 8192, 128, 32, 64, 17
+    P = hb.synthetic(n, ls, r, seed, device=local, shard_rank=rank, n_shards=world)
+    uid = [hb.PackedHss.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, src=0)
+    P.comm_init(uid[0], rank, world)
+    rows = P.info.local_n
+    X = o.synth_x(seed, n, k, P.info.local_col0, rows)
+    Y = P @ X
+    ref = o.matmul(o.synthetic_hss(n, ls, r, seed), o.synth_x(seed, n, k))
+    mine = ref[P.info.local_row0:P.info.local_row0 + P.info.local_m]
+    err = np.linalg.norm(Y - mine) / np.linalg.norm(mine)
+    t = torch.tensor([err], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    P.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("SHARDED_OK" if t.item() <= 1e-12 else f"SHARDED_FAIL {t.item():.3e}")
+    if t.item() > 1e-12:
+        sys.exit(1)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,195 @@
+"""CPU tests of the native packer + level scheduler (no GPU): the plan the
+library would launch is executed by a numpy interpreter and compared with the
+oracle restatement of src/matmul.jl:18-62."""
+import numpy as np
+import pytest
+
+import plan_interp
+
+TOL = 1e-12  # BASELINE.json north_star: relative Frobenius error
+
+
+def relerr(a, b):
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def to_product_tree(hb, h):
+    """oracle tree -> product HssMatrix (same field names, distinct class)."""
+    if h.leafnode:
+        t = hb.HssMatrix.leaf(h.D, h.U, h.V, rootnode=h.rootnode)
+        return t
+    return hb.HssMatrix.branch(to_product_tree(hb, h.A11), to_product_tree(hb, h.A22), h.B12, h.B21,
+                               h.R1, h.W1, h.R2, h.W2, rootnode=h.rootnode)
+
+
+CASES = [  # (n, leafsize, nrhs, rmin, rmax)
+    (2001, 64, 16, 1, 6),   # README shape: 32 leaves of 62/63 rows
+    (777, 50, 5, 1, 9),     # odd sizes (48/49-row leaves)
+    (1024, 64, 64, 3, 3),
+    (100, 200, 3, 1, 3),    # root is a leaf: plain GEMM (matmul.jl:21-22)
+    (130, 64, 1, 0, 2),     # ranks may be 0 (hss_blkdiag)
+    (5, 1, 2, 1, 2),        # 1x1 leaves
+]
+
+
+@pytest.mark.parametrize("n,leafsize,nrhs,rmin,rmax", CASES)
+def test_plan_matches_oracle(hb, oracle, n, leafsize, nrhs, rmin, rmax):
+    rng = np.random.default_rng(n * 7 + leafsize)
+    cl = oracle.bisection_cluster(n, leafsize)
+    h = oracle.random_hss(cl, cl, rng, rmin, rmax)
+    X = rng.standard_normal((n, nrhs))
+    ref = oracle.matmul(h, X)
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    Y = np.full((n, nrhs), np.nan, order="F")  # beta = 0 must never read Y
+    plan_interp.run_plan(P, X, Y)
+    assert relerr(Y, ref) <= TOL
+    b, f = oracle.algorithmic_counts(h, nrhs)
+    assert P.flops(nrhs) == f
+    assert P.algorithmic_bytes(nrhs) == b
+
+
+def test_alpha_beta(hb, oracle):
+    rng = np.random.default_rng(5)
+    cl = oracle.bisection_cluster(300, 40)
+    h = oracle.random_hss(cl, cl, rng)
+    X = rng.standard_normal((300, 4))
+    C0 = rng.standard_normal((300, 4))
+    ref = oracle.mul(C0.copy(), h, X, 0.7, -1.3)
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    Y = np.asfortranarray(C0.copy())
+    plan_interp.run_plan(P, X, Y, 0.7, -1.3)
+    assert relerr(Y, ref) <= TOL
+
+
+def test_rectangular_and_unbalanced(hb, oracle):
+    """m != n per node, different row/col ranks, leaves at different depths
+    (prune_leaves!, hssmatrix.jl:325-335) — none of which the reference tests."""
+    rng = np.random.default_rng(11)
+    rcl = oracle.bisection_cluster(500, 70)
+    ccl = oracle.bisection_cluster(333, 47)  # same tree shape (8 leaves), different sizes
+    h = oracle.random_hss(rcl, ccl, rng, 1, 7)
+    h.A11 = oracle.prune_leaves(h.A11)
+    h.sz1 = oracle.size(h.A11)
+    h.A22.A11 = oracle.prune_leaves(h.A22.A11)
+    h.A22.sz1 = oracle.size(h.A22.A11)
+    X = rng.standard_normal((333, 6))
+    ref = oracle.full(h) @ X
+    assert relerr(oracle.matmul(h, X), ref) <= TOL
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    assert P.shape == (500, 333)
+    Y = np.full((500, 6), np.nan, order="F")
+    plan_interp.run_plan(P, X, Y)
+    assert relerr(Y, ref) <= TOL
+
+
+def test_subblock_is_rooted(hb, oracle):
+    """matmul.jl:24: multiplying a sub-block ignores its own translators."""
+    rng = np.random.default_rng(3)
+    cl = oracle.bisection_cluster(512, 64)
+    h = oracle.random_hss(cl, cl, rng)
+    sub = h.A11
+    X = rng.standard_normal((256, 3))
+    ref = oracle.matmul(sub, X)
+    P = hb.pack(to_product_tree(hb, sub), plan_only=True)
+    Y = np.zeros((256, 3), order="F")
+    plan_interp.run_plan(P, X, Y)
+    assert relerr(Y, ref) <= TOL
+
+
+def test_synthetic_twin_bit_identical(hb, oracle):
+    """The library's host twin of the device generator produces the same bits
+    as oracle.synthetic_hss, block by block."""
+    n, ls, r, seed = 1024, 128, 8, 42
+    h = oracle.synthetic_hss(n, ls, r, seed)
+    P = hb.synthetic(n, ls, r, seed, plan_only=True)
+    assert P.info.uniform == 1 and P.info.n_leaves == 8
+
+    def walk(t, node):
+        nd = P.node(node)
+        if t.leafnode:
+            assert nd.is_leaf
+            assert np.array_equal(P.block(node, "D"), t.D)
+            assert np.array_equal(P.block(node, "U"), t.U)
+            assert np.array_equal(P.block(node, "V"), t.V)
+            return
+        assert np.array_equal(P.block(node, "B12"), t.B12)
+        assert np.array_equal(P.block(node, "B21"), t.B21)
+        if t.R1.shape[1]:
+            assert np.array_equal(P.block(nd.left, "R"), t.R1)
+            assert np.array_equal(P.block(nd.right, "R"), t.R2)
+            assert np.array_equal(P.block(nd.left, "W"), t.W1)
+            assert np.array_equal(P.block(nd.right, "W"), t.W2)
+        walk(t.A11, nd.left)
+        walk(t.A22, nd.right)
+
+    walk(h, 0)
+    X = oracle.synth_x(seed, n, 4)
+    Y = np.zeros((n, 4), order="F")
+    plan_interp.run_plan(P, X, Y)
+    assert relerr(Y, oracle.matmul(h, X)) <= TOL
+    assert (P.algorithmic_bytes(4), P.flops(4)) == oracle.synthetic_counts(n, ls, r, 4)
+
+
+@pytest.mark.parametrize("P_", [2, 4, 8])
+def test_sharded_plan(hb, oracle, P_):
+    """Subtree sharding: P plans + one all-gather reproduce the
+    single-shard product; every shard only holds its own leaves."""
+    n, ls, r, seed, k = 2048, 64, 6, 9, 5
+    h = oracle.synthetic_hss(n, ls, r, seed)
+    X = oracle.synth_x(seed, n, k)
+    ref = oracle.matmul(h, X)
+    packs = [hb.synthetic(n, ls, r, seed, shard_rank=g, n_shards=P_, plan_only=True) for g in range(P_)]
+    rows = n // P_
+    Xs = [X[g * rows:(g + 1) * rows] for g in range(P_)]
+    Ys = [np.full((rows, k), np.nan, order="F") for _ in range(P_)]
+    for g, p in enumerate(packs):
+        assert p.local_shape == (rows, rows) and p.info.local_row0 == g * rows
+        assert p.info.n_leaves == (n // ls) // P_
+    plan_interp.run_sharded(packs, Xs, Ys)
+    assert relerr(np.vstack(Ys), ref) <= TOL
+
+
+def test_sharded_from_host_tree(hb, oracle):
+    """Same through the builder path (hssb_builder_add_remote placeholders),
+    with variable ranks."""
+    rng = np.random.default_rng(21)
+    n, k = 1000, 3
+    cl = oracle.bisection_cluster(n, 70)
+    h = oracle.random_hss(cl, cl, rng, 2, 7)
+    X = rng.standard_normal((n, k))
+    ref = oracle.matmul(h, X)
+    tree = to_product_tree(hb, h)
+    packs = [hb.pack(tree, shard_rank=g, n_shards=4, plan_only=True) for g in range(4)]
+    Xs, Ys = [], []
+    for p in packs:
+        r0, m = p.info.local_col0, p.info.local_n
+        Xs.append(X[r0:r0 + m])
+        Ys.append(np.full((p.info.local_m, k), np.nan, order="F"))
+    plan_interp.run_sharded(packs, Xs, Ys)
+    assert relerr(np.vstack(Ys), ref) <= TOL
+
+
+def test_dimension_mismatch(hb, oracle):
+    rng = np.random.default_rng(1)
+    cl = oracle.bisection_cluster(64, 16)
+    tree = to_product_tree(hb, oracle.random_hss(cl, cl, rng))
+    with pytest.raises(hb.DimensionMismatch):  # matmul.jl:19
+        hb.mul_(np.zeros((64, 2), order="F"), tree, np.zeros((63, 2)))
+    with pytest.raises(hb.DimensionMismatch):  # matmul.jl:20
+        hb.mul_(np.zeros((64, 3), order="F"), tree, np.zeros((64, 2)))
+    with pytest.raises(hb.DimensionMismatch):  # hssmatrix.jl:58
+        hb.HssMatrix.branch(tree.A11, tree.A22, tree.B12, tree.B21, np.zeros((1, 2)), np.zeros((1, 2)),
+                            np.zeros((1, 3)), np.zeros((1, 2)))
+    # builder-level checks: wrong shard layout
+    with pytest.raises(hb.HssbError):
+        hb.pack(tree, shard_rank=0, n_shards=64, plan_only=True)
+
+
+def test_no_cpu_fallback(hb, oracle):
+    """A plan-only handle (or a box without a B200) must fail loudly."""
+    P = hb.synthetic(256, 64, 4, 1, plan_only=True)
+    with pytest.raises(hb.HssbError):
+        P @ np.zeros((256, 2))
+    if hb.device_count() == 0:
+        with pytest.raises(hb.HssbError):
+            hb.synthetic(256, 64, 4, 1)
