@@ -191,7 +191,10 @@ def main():
         P.set_option(hb.OPT_FUSED_LEAF, 1)
     P.set_option(hb.OPT_USE_GRAPH, 0 if ("nograph" in variants or N > 1) else 1)
     rows = P.info.local_n
-    st = torch.cuda.current_stream().cuda_stream
+    # a dedicated non-default stream: the library launches on it and torch's events time it
+    tstream = torch.cuda.Stream()
+    torch.cuda.set_stream(tstream)
+    st = tstream.cuda_stream
     X = torch.empty((k, rows), dtype=torch.float64, device="cuda")  # column-major rows x k
     Y = torch.empty((k, rows), dtype=torch.float64, device="cuda")
     hb._check(hb.lib().hssb_synthetic_rhs(SEED, n_total, k, P.info.local_col0, rows, X.data_ptr(), rows, local, st))

@@ -706,9 +706,11 @@ static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
   if (H->graphs.size() >= 16) invalidate_graphs(H);
   cudaGraph_t graph = nullptr;
   const int64_t before = H->launches;
-  HSSB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  int rc = run_phases(H, cp, st);
-  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  // capture on the library's own stream (the legacy default stream cannot be captured),
+  // replay on the caller's stream
+  HSSB_CUDA(cudaStreamBeginCapture(H->stream, cudaStreamCaptureModeThreadLocal));
+  int rc = run_phases(H, cp, H->stream);
+  cudaError_t e = cudaStreamEndCapture(H->stream, &graph);
   const int64_t kernels = H->launches - before;
   H->launches = before;
   if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -951,7 +953,7 @@ int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs
   if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
   int rc = ensure_workspace(h, nrhs);
   if (rc) return rc;
-  cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+  cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   CallParams cp;
   cp.pool = h->pool_dev; cp.X = dX; cp.Y = dY; cp.Z = h->z_dev; cp.F = h->f_dev;
   cp.ldx = ldx; cp.ldy = ldy; cp.nrhs = (int32_t)nrhs; cp.alpha = alpha; cp.beta = beta;

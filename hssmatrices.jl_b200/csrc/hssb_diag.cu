@@ -38,6 +38,23 @@ __global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, 
   if (s == 123.456) out[0] = s;
 }
 
+// DMMA throughput with ONE CTA per SM of blockDim.x threads and 16 independent accumulator tiles
+// per warp (the leaf-down inner loop shape): how many warps per scheduler saturate the FP64 pipe?
+__global__ void __launch_bounds__(128) dmma_occupancy_kernel(double* out, int iters, double seed) {
+  double c[16][2];
+  const double a = seed + threadIdx.x * 1e-9, b = 1e-3 * seed;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) c[i][0] = c[i][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) mma_m8n8k4(c[i][0], c[i][1], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += c[i][0] + c[i][1];
+  if (s == 123.456) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
@@ -80,6 +97,24 @@ extern "C" int hssb_measure_peak(int device, int kind, int64_t arg, double* out)
       HSSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       // DFMA: 8 FMAs/thread/iter; DMMA: 8 m8n8k4 (= 512 flops) per warp per iter
       const double flops = kind == 0 ? 2.0 * 8 * iters * 256.0 * grid : 8.0 * 512.0 * iters * 8.0 * grid;
+      if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaFree(d);
+  } else if (kind == 3) {
+    // arg = warps per SM sub-partition: CTAs of 128 threads (one warp per scheduler), arg CTAs per SM
+    const int threads = 128;
+    const int iters = 4000;
+    const int grid = prop.multiProcessorCount * (int)((arg >= 1 && arg <= 16) ? arg : 1);
+    double* d = nullptr;
+    HSSB_CUDA(cudaMalloc(&d, 64));
+    for (int rep = 0; rep < 4; ++rep) {
+      HSSB_CUDA(cudaEventRecord(e0));
+      dmma_occupancy_kernel<<<grid, threads>>>(d, iters, 0.5);
+      HSSB_CUDA(cudaEventRecord(e1));
+      HSSB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      HSSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double flops = 16.0 * 512.0 * iters * (threads / 32.0) * grid;
       if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
     }
     cudaFree(d);

@@ -143,8 +143,8 @@ int hssb_reserve(hssb_matrix* h, int64_t max_nrhs);
 int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
                 const double* X, int64_t ldx, double* Y, int64_t ldy, double alpha, double beta);
 
-/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t, NULL =
- * the library's own stream).  This is the timed entry.                       */
+/* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t; NULL =
+ * the CUDA default stream).  This is the timed entry.                        */
 int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
                     const double* dX, int64_t ldx, double* dY, int64_t ldy, double alpha, double beta,
                     void* stream);

@@ -102,7 +102,10 @@ def test_synthetic_device_generated(gpu, oracle, n, ls, r, k):
     with gpu.synthetic(n, ls, r, seed) as P:
         nd = P.node(0)
         assert np.array_equal(P.block(0, "B12"), h.B12)
-        assert np.array_equal(P.block(nd.left, "W"), h.A11.W1 if not h.A11.leafnode else np.zeros((r, 0)))
+        assert P.block(nd.left, "W").shape == (r, 0)   # children of the root carry no translators
+        if not h.A11.leafnode:
+            assert np.array_equal(P.block(P.node(nd.left).left, "W"), h.A11.W1)
+            assert np.array_equal(P.block(P.node(nd.left).right, "R"), h.A11.R2)
         leaf = h
         node = 0
         while not leaf.leafnode:
@@ -127,6 +130,7 @@ def test_device_entry_and_synthetic_rhs(gpu, oracle):
     with gpu.synthetic(n, ls, r, seed) as P:
         X = torch.zeros((k, ldx), dtype=torch.float64, device="cuda")   # column-major n x k, ld = ldx
         Y = torch.full((k, ldy), float("nan"), dtype=torch.float64, device="cuda")
+        torch.cuda.synchronize()
         st = torch.cuda.current_stream().cuda_stream
         rc = gpu.lib().hssb_synthetic_rhs(seed, n, k, 0, n, X.data_ptr(), ldx, 0, st)
         assert rc == 0
