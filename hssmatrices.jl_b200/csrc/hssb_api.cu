@@ -111,7 +111,7 @@ static void block_shape(const std::vector<Node>& nodes, const Node& t, int kind,
   switch (kind) {
     case BK_D: if (t.leaf && !t.remote) { rows = t.m; cols = t.n; } break;
     case BK_U: if (t.leaf && !t.remote) { rows = t.m; cols = t.kr; } break;
-    case BK_V: if (t.leaf && !t.remote) { rows = t.n; cols = t.kw; } break;
+    case BK_V: if (t.leaf && !t.remote) { rows = t.kw; cols = t.n; } break;  // stored TRANSPOSED (V' is kw x n): every A operand is then column-major "N"
     case BK_B12: if (!t.leaf && !t.remote) { rows = nodes[(size_t)t.left].kr; cols = nodes[(size_t)t.right].kw; } break;
     case BK_B21: if (!t.leaf && !t.remote) { rows = nodes[(size_t)t.right].kr; cols = nodes[(size_t)t.left].kw; } break;
     case BK_R: if (par) { rows = t.kr; cols = par->kr; } break;
@@ -272,7 +272,7 @@ static void build_plan(hssb_matrix* H) {
     const Node& t = nodes[(size_t)li];
     if (t.parent < 0 || t.kw == 0) continue;
     GTask g = blank();
-    g.a0 = t.off[BK_V]; g.lda0 = t.ld[BK_V]; g.ta0 = 1;
+    g.a0 = t.off[BK_V]; g.lda0 = t.ld[BK_V]; g.ta0 = 0;  // the pool holds V' (kw x n)
     g.sb0 = SRC_X; g.b0 = t.col0 - c0;
     g.M = (int32_t)t.kw; g.K0 = (int32_t)t.n; g.K1 = 0;
     g.sc = SRC_Z; g.c = t.zoff; g.ldc = t.ldz;
@@ -437,11 +437,20 @@ static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src) {
       HSSB_CUDA(cudaMallocHost(&stage[i], CH * sizeof(double)));
       HSSB_CUDA(cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming));
     }
-    struct Piece { int64_t off; const HostBlock* hb; int32_t ld; };
+    struct Piece { int64_t off; const HostBlock* hb; int32_t ld; bool tr; int64_t rows, cols; };  // rows/cols as stored
     std::vector<Piece> pieces;
     for (size_t i = 0; i < nodes.size(); ++i)
       for (int k = 0; k < BK_COUNT; ++k)
-        if (nodes[i].off[k] >= 0) pieces.push_back({nodes[i].off[k], (*src)[i].blk[k], nodes[i].ld[k]});
+        if (nodes[i].off[k] >= 0)
+          pieces.push_back({nodes[i].off[k], (*src)[i].blk[k], nodes[i].ld[k], k == BK_V, nodes[i].rows[k], nodes[i].cols[k]});
+    auto put = [](double* dst, const Piece& pc) {  // dst has leading dimension pc.ld
+      if (!pc.tr) {
+        for (int64_t j = 0; j < pc.cols; ++j) memcpy(dst + j * pc.ld, pc.hb->data.data() + j * pc.rows, (size_t)pc.rows * sizeof(double));
+      } else {  // stored(i, j) = host(j, i), host is cols x rows with leading dimension cols
+        for (int64_t j = 0; j < pc.cols; ++j)
+          for (int64_t i = 0; i < pc.rows; ++i) dst[j * pc.ld + i] = pc.hb->data[(size_t)(i * pc.cols + j)];
+      }
+    };
     std::sort(pieces.begin(), pieces.end(), [](const Piece& a, const Piece& b) { return a.off < b.off; });
     size_t pi = 0;
     int cur = 0;
@@ -453,19 +462,17 @@ static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src) {
       memset(stage[cur], 0, CH * sizeof(double));
       while (pj < pieces.size()) {
         const Piece& pc = pieces[pj];
-        const int64_t pend = pc.off + (int64_t)pc.ld * pc.hb->cols;
+        const int64_t pend = pc.off + (int64_t)pc.ld * pc.cols;
         if (pend - base > (int64_t)CH) break;
-        for (int64_t j = 0; j < pc.hb->cols; ++j)
-          memcpy(stage[cur] + (pc.off - base) + j * pc.ld, pc.hb->data.data() + j * pc.hb->rows,
-                 (size_t)pc.hb->rows * sizeof(double));
+        put(stage[cur] + (pc.off - base), pc);
         end = pend;
         ++pj;
       }
-      if (pj == pi) {  // single block larger than a chunk: upload it column by column
+      if (pj == pi) {  // single block larger than a chunk: upload it on its own
         const Piece& pc = pieces[pi];
-        HSSB_CUDA(cudaMemcpy2DAsync(H->pool_dev + pc.off, (size_t)pc.ld * 8, pc.hb->data.data(), (size_t)pc.hb->rows * 8,
-                                    (size_t)pc.hb->rows * 8, (size_t)pc.hb->cols, cudaMemcpyHostToDevice, H->stream));
-        HSSB_CUDA(cudaStreamSynchronize(H->stream));
+        std::vector<double> tmp((size_t)pc.ld * (size_t)pc.cols, 0.0);
+        put(tmp.data(), pc);
+        HSSB_CUDA(cudaMemcpy(H->pool_dev + pc.off, tmp.data(), tmp.size() * sizeof(double), cudaMemcpyHostToDevice));
         ++pi;
         continue;
       }
@@ -488,6 +495,7 @@ static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src) {
           b.off = t.off[k];
           b.key = synth_key(H->seed, t.heap_id, k);
           b.rows = (int32_t)t.rows[k]; b.cols = (int32_t)t.cols[k]; b.ld = t.ld[k];
+          b.transposed = (k == BK_V);
           b.c = IH4_SCALE * ((k == BK_R || k == BK_W) ? tscale : 1.0);
           sb.push_back(b);
         }
@@ -583,15 +591,18 @@ static void fill_pool_host(hssb_matrix* H, const std::vector<BlockSource>* src) 
     for (int k = 0; k < BK_COUNT; ++k) {
       if (t.off[k] < 0) continue;
       double* dst = H->pool_host.data() + t.off[k];
+      const bool tr = (k == BK_V);  // stored(i, j) = logical(j, i); logical block is cols x rows
       if (src) {
         const HostBlock* hb = (*src)[i].blk[k];
         for (int64_t j = 0; j < t.cols[k]; ++j)
-          memcpy(dst + j * t.ld[k], hb->data.data() + j * hb->rows, (size_t)t.rows[k] * sizeof(double));
+          for (int64_t r = 0; r < t.rows[k]; ++r)
+            dst[j * t.ld[k] + r] = tr ? hb->data[(size_t)(r * t.cols[k] + j)] : hb->data[(size_t)(j * t.rows[k] + r)];
       } else {
         const uint64_t key = synth_key(H->seed, t.heap_id, k);
         const double c = IH4_SCALE * ((k == BK_R || k == BK_W) ? tscale : 1.0);
         for (int64_t j = 0; j < t.cols[k]; ++j)
-          for (int64_t r = 0; r < t.rows[k]; ++r) dst[j * t.ld[k] + r] = synth_value(key, (uint64_t)(j * t.rows[k] + r), c);
+          for (int64_t r = 0; r < t.rows[k]; ++r)
+            dst[j * t.ld[k] + r] = synth_value(key, (uint64_t)(tr ? r * t.cols[k] + j : j * t.rows[k] + r), c);
       }
     }
   }
@@ -912,18 +923,25 @@ int hssb_get_block(const hssb_matrix* h, int64_t node, int kind, double* out, in
   if (node < 0 || node >= (int64_t)h->nodes.size() || kind < 0 || kind >= BK_COUNT)
     HSSB_FAIL(HSSB_ERR_ARG, "hssb_get_block: bad node or kind");
   const Node& t = h->nodes[(size_t)node];
-  const int64_t rows = t.rows[kind], cols = t.cols[kind];
+  const int64_t rows = t.rows[kind], cols = t.cols[kind];  // as stored
   if (out_len < rows * cols) HSSB_FAIL(HSSB_ERR_ARG, "hssb_get_block: need %lld doubles", (long long)(rows * cols));
   if (rows * cols == 0 || t.off[kind] < 0) return HSSB_OK;
   if (!out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_get_block: out is NULL");
+  std::vector<double> tmp((size_t)(rows * cols));
   if (h->device < 0) {
     for (int64_t j = 0; j < cols; ++j)
-      memcpy(out + j * rows, h->pool_host.data() + t.off[kind] + j * t.ld[kind], (size_t)rows * 8);
-    return HSSB_OK;
+      memcpy(tmp.data() + j * rows, h->pool_host.data() + t.off[kind] + j * t.ld[kind], (size_t)rows * 8);
+  } else {
+    DeviceGuard dg(h->device);
+    HSSB_CUDA(cudaMemcpy2D(tmp.data(), (size_t)rows * 8, h->pool_dev + t.off[kind], (size_t)t.ld[kind] * 8, (size_t)rows * 8,
+                           (size_t)cols, cudaMemcpyDeviceToHost));
   }
-  DeviceGuard dg(h->device);
-  HSSB_CUDA(cudaMemcpy2D(out, (size_t)rows * 8, h->pool_dev + t.off[kind], (size_t)t.ld[kind] * 8, (size_t)rows * 8,
-                         (size_t)cols, cudaMemcpyDeviceToHost));
+  if (kind == BK_V) {  // the pool holds V' (kw x n); hand back V (n x kw)
+    for (int64_t j = 0; j < cols; ++j)
+      for (int64_t i = 0; i < rows; ++i) out[i * cols + j] = tmp[(size_t)(j * rows + i)];
+  } else {
+    memcpy(out, tmp.data(), tmp.size() * 8);
+  }
   return HSSB_OK;
 }
 

@@ -12,10 +12,10 @@
 // packer guarantees it).
 //
 // Kernels
-//   leaf_up_kernel<M,R>    Z  = V' X          persistent, X resident, V streamed by column chunks
-//   merge_kernel<R>        Z  = W1' Z1 + W2' Z2                    one CTA per (node, column tile)
-//   translate_kernel<R>    F1 = B12 Z2 + R1 F ; F2 = B21 Z1 + R2 F  one CTA per (parent, column tile)
-//   leaf_down_kernel<M,R>  Y  = a (D X + U F) + b Y   persistent, X resident, [D U] streamed by K chunks
+//   stream_leaf_kernel<M,R,false>  Z = V' X               persistent, warp-specialised (TMA producer warp)
+//   stream_leaf_kernel<M,R,true>   Y = a (D X + U F) + b Y   same kernel, [D U] streamed by K chunks
+//   merge_kernel<R>                Z = W1' Z1 + W2' Z2                   one CTA per (node, column tile)
+//   translate_kernel<R>            F1 = B12 Z2 + R1 F ; F2 = B21 Z1 + R2 F   one CTA per (parent, tile)
 #pragma once
 
 #include "hssb_internal.h"
@@ -47,232 +47,272 @@ __device__ __forceinline__ void copy_block_async(double* dst, int ldd, const dou
   }
 }
 
+// ------------------------------------------------- TMA bulk copy + mbarrier ---
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (and surface as a CUDA error), never hang the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000ll) __trap();
+  }
+}
+// 1-D bulk copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier.
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ------------------------------------------------------------- leaf shapes ---
-template <int M, int R>
-struct LeafCfg {
-  static constexpr int WM = M / 32;       // warps along the leaf rows (leaf-down)
-  static constexpr int WN = 8 / WM;       // warps along the right-hand sides
-  static constexpr int NT = 32 * WN;      // right-hand sides per tile
-  static constexpr int LDX = M + 4, LDF = R + 4, LDA = M + 4;
-  // leaf-down: [D U] streamed in K chunks of KC columns (M x KC, contiguous in the pool)
-  static constexpr int KC = (M >= 256) ? 8 : 16;
-  static constexpr int NSTAGE = 3;
-  static constexpr int NCH_D = M / KC, NCH_U = R / KC, NCH = NCH_D + NCH_U;
-  static constexpr int XPIECE = (NT + (NCH - 2) - 1) / (NCH - 2);  // X columns prefetched per chunk group
-  static constexpr size_t DOWN_SMEM = sizeof(double) * (2 * NT * LDX + NT * LDF + NSTAGE * KC * LDA);
-  // leaf-up: V streamed in chunks of VC columns (M x VC, contiguous); one 8x8 output tile per warp and chunk
-  static constexpr int VC = 64 / (NT / 8);  // (NT/8) * (VC/8) == 8 tiles per chunk
-  static constexpr int NVC = R / VC;
-  static constexpr int UP_STAGES = (M >= 256) ? 2 : (NVC + 1 < 4 ? NVC + 1 : 4);  // needs UP_STAGES - 1 <= NVC
-  static constexpr size_t UP_SMEM = sizeof(double) * (2 * NT * LDX + UP_STAGES * VC * LDA);
-  static_assert(M % 32 == 0 && WM * WN == 8 && R % KC == 0 && VC % 8 == 0 && R % VC == 0 && NCH_D > 2 &&
-                    UP_STAGES >= 2 && UP_STAGES - 1 <= NVC, "unsupported leaf shape");
+// Both leaf kernels are one template: a persistent, warp-specialised, streamed-A GEMM
+//     OUT[MO x NT] = [A0 | A1] * [X ; F]           (K = K0 + K1)
+//   leaf down:  MO = M, A0 = D (M x M),   A1 = U (M x R), OUT -> Y = alpha*OUT + beta*Y
+//   leaf up:    MO = R, A0 = V' (R x M),  no A1,          OUT -> Z
+// X (K0 x NT, the user's columns) is resident and double buffered across items; [A0 | A1] is
+// streamed through an NSTAGE ring in chunks of KC columns (MO x KC, contiguous in the pool).
+// Warp 8 is the producer: it issues one cp.async.bulk per column (so the shared-memory image can
+// carry the conflict-free +4 padding) and tracks completion in bytes on mbarriers.  Warps 0-7
+// only wait, load fragments and issue DMMAs; they hand buffers back through "empty" mbarriers.
+template <int M, int R, bool DOWN>
+struct StreamCfg {
+  static constexpr int MO = DOWN ? M : R;
+  static constexpr int K0 = M, K1 = DOWN ? R : 0;
+  static constexpr int NT = DOWN ? 8192 / M : (M >= 256 ? 32 : 64);  // same tile as leaf-down so both share X tiles
+  static constexpr int WR = DOWN ? M / 32 : ((R >= 32 ? 2 : 1) > 64 / NT ? (R >= 32 ? 2 : 1) : 64 / NT);  // warps along OUT rows
+  static constexpr int WC = 8 / WR;                                  // warps along right-hand sides
+  static constexpr int TM = MO / WR / 8, TN = NT / WC / 8;           // DMMA tiles per warp
+  static constexpr int KC = DOWN ? (M >= 256 ? 8 : 16) : (4096 / R > M ? M : 4096 / R);
+  static constexpr int NSTAGE = DOWN ? 3 : 2;
+  static constexpr int NCH0 = K0 / KC, NCH1 = K1 / KC, NCH = NCH0 + NCH1;
+  static constexpr int LDX = K0 + 4, LDF = K1 + 4, LDA = MO + 4;
+  static constexpr int CX = (NSTAGE < NCH0 - 1) ? NSTAGE : NCH0 - 1;  // chunk after which F(i) and X(i+1) are issued
+  static constexpr int BAR_BYTES = 128;
+  static constexpr size_t SMEM = BAR_BYTES + sizeof(double) * (2 * NT * LDX + (K1 ? NT * LDF : 0) + NSTAGE * KC * LDA);
+  static_assert(MO % (8 * WR) == 0 && NT % (8 * WC) == 0 && TM >= 1 && TN >= 1, "warp tiling");
+  static_assert(K0 % KC == 0 && K1 % KC == 0 && KC % 4 == 0 && NCH0 >= 1, "chunking");
+  static_assert(SMEM <= 232448, "shared memory budget");
 };
 
-// =============================================================== leaf down ===
-// Y[M x NT] = alpha * ([D U] * [X; F]) + beta * Y for one (leaf, column tile) item at a time.
-// Persistent CTA (one per SM), 8 warps, warp tile 32 x 32 (4x4 DMMA tiles, 32 accumulators/lane).
-// Pipeline of cp.async groups, one per K chunk: group (item, c) carries the A chunk c, the F block
-// of the item (c == 2) and a slice of the NEXT item's X block (c >= 2), so the X block of item i+1
-// is resident before item i ends and the FP64 pipe never waits at an item boundary.
-template <int M, int R>
-__global__ void __launch_bounds__(256, 1)
-leaf_down_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p) {
-  using C = LeafCfg<M, R>;
-  extern __shared__ __align__(16) double smem[];
-  double* Xs = smem;                       // [2][NT][LDX]
-  double* Fs = Xs + 2 * C::NT * C::LDX;    // [NT][LDF]
-  double* As = Fs + C::NT * C::LDF;        // [NSTAGE][KC][LDA]
+template <int M, int R, bool DOWN>
+__global__ void __launch_bounds__(288, 1)
+stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p) {
+  using C = StreamCfg<M, R, DOWN>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  uint64_t* a_full = bars;                    // [NSTAGE]
+  uint64_t* a_empty = bars + C::NSTAGE;       // [NSTAGE]
+  uint64_t* x_full = bars + 2 * C::NSTAGE;    // [2]
+  uint64_t* x_empty = x_full + 2;             // [2]
+  uint64_t* f_full = x_empty + 2;             // [1]
+  uint64_t* f_empty = f_full + 1;             // [1]
+  double* Xs = reinterpret_cast<double*>(smem_raw + C::BAR_BYTES);  // [2][NT][LDX]
+  double* Fs = Xs + 2 * C::NT * C::LDX;                             // [NT][LDF]
+  double* As = Fs + (C::K1 ? C::NT * C::LDF : 0);                   // [NSTAGE][KC][LDA]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  const int wm = warp % C::WM, wn = warp / C::WM;
   const int nitems = ntasks * ntiles;
   const int first = (int)(((int64_t)blockIdx.x * nitems) / gridDim.x);
   const int last = (int)(((int64_t)(blockIdx.x + 1) * nitems) / gridDim.x);
   const int my = last - first;
-  if (my <= 0) return;
-  const int G = my * C::NCH;
   const int nrhs = p.nrhs;
 
+  if (tid == 0) {
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 8); }
+    mbar_init(f_full, 1);
+    mbar_init(f_empty, 8);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (my <= 0) return;
+
   auto item_cols = [&](int item) { return min(C::NT, nrhs - ((first + item) % ntiles) * C::NT); };
-  auto load_x = [&](int item, int c0, int c1) {  // columns [c0, c1) of the item's X block
-    const GTask& tk = tasks[(first + item) / ntiles];
-    const int tile = (first + item) % ntiles;
-    c1 = min(c1, item_cols(item));
-    if (c0 >= c1) return;
-    const double* src = p.X + tk.b0 + (int64_t)(tile * C::NT + c0) * p.ldx;
-    copy_block_async<256>(Xs + (item & 1) * C::NT * C::LDX + c0 * C::LDX, C::LDX, src, p.ldx, M, c1 - c0, tid);
-  };
-  auto issue_group = [&](int gi) {
-    if (gi < G) {
-      const int item = gi / C::NCH, c = gi - item * C::NCH;
+
+  if (warp == 8) {
+    // ====================== producer warp ======================
+    auto load_x = [&](int item) {
       const GTask& tk = tasks[(first + item) / ntiles];
-      const double* asrc = p.pool + (c < C::NCH_D ? tk.a0 + (int64_t)c * C::KC * M : tk.a1 + (int64_t)(c - C::NCH_D) * C::KC * M);
-      copy_block_async<256>(As + (gi % C::NSTAGE) * C::KC * C::LDA, C::LDA, asrc, M, M, C::KC, tid);
-      if (c == 2) {
-        const int tile = (first + item) % ntiles;
-        const double* fsrc = p.F + tk.b1 * (int64_t)nrhs + (int64_t)tile * C::NT * R;
-        copy_block_async<256>(Fs, C::LDF, fsrc, R, R, item_cols(item), tid);
+      const int tile = (first + item) % ntiles, nc = item_cols(item), buf = item & 1;
+      mbar_wait(&x_empty[buf], ((item >> 1) & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(&x_full[buf], (uint32_t)(nc * C::K0 * 8));
+      __syncwarp();
+      const double* src = p.X + tk.b0 + (int64_t)tile * C::NT * p.ldx;
+      double* dst = Xs + buf * C::NT * C::LDX;
+      for (int c = lane; c < nc; c += 32) bulk_g2s(dst + c * C::LDX, src + (int64_t)c * p.ldx, C::K0 * 8, &x_full[buf]);
+    };
+    auto load_f = [&](int item) {
+      if (C::K1 == 0) return;
+      const GTask& tk = tasks[(first + item) / ntiles];
+      const int tile = (first + item) % ntiles, nc = item_cols(item);
+      mbar_wait(f_empty, (item & 1) ^ 1);
+      if (lane == 0) mbar_expect_tx(f_full, (uint32_t)(nc * C::K1 * 8));
+      __syncwarp();
+      const double* src = p.F + tk.b1 * (int64_t)nrhs + (int64_t)tile * C::NT * C::K1;
+      for (int c = lane; c < nc; c += 32) bulk_g2s(Fs + c * C::LDF, src + (int64_t)c * C::K1, C::K1 * 8, f_full);
+    };
+    load_x(0);
+    int g = 0;
+    for (int item = 0; item < my; ++item) {
+      const GTask& tk = tasks[(first + item) / ntiles];
+      for (int c = 0; c < C::NCH; ++c, ++g) {
+        const int st = g % C::NSTAGE;
+        mbar_wait(&a_empty[st], ((g / C::NSTAGE) & 1) ^ 1);
+        if (lane == 0) mbar_expect_tx(&a_full[st], (uint32_t)(C::KC * C::MO * 8));
+        __syncwarp();
+        const double* src = p.pool + (c < C::NCH0 ? tk.a0 + (int64_t)c * C::KC * C::MO : tk.a1 + (int64_t)(c - C::NCH0) * C::KC * C::MO);
+        double* dst = As + st * C::KC * C::LDA;
+        for (int col = lane; col < C::KC; col += 32) bulk_g2s(dst + col * C::LDA, src + (int64_t)col * C::MO, C::MO * 8, &a_full[st]);
+        if (c == C::CX) {
+          load_f(item);
+          if (item + 1 < my) load_x(item + 1);
+        }
       }
-      if (c >= 2 && item + 1 < my) load_x(item + 1, (c - 2) * C::XPIECE, (c - 1) * C::XPIECE);
     }
-    cp_async_commit();
-  };
+    return;
+  }
 
-  // prologue: X of the first item, then the first NSTAGE-1 chunk groups
-  load_x(0, 0, C::NT);
-  cp_async_commit();
-  issue_group(0);
-  issue_group(1);
-
-  double acc[4][4][2];
+  // ====================== consumer warps ======================
+  const int gq = lane >> 2, t = lane & 3;
+  const int wr = warp % C::WR, wc = warp / C::WR;
+  double acc[C::TM][C::TN][2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < C::TM; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int j = 0; j < C::TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  for (int gi = 0; gi < G; ++gi) {
-    cp_async_wait<1>();   // group gi (and everything older) has landed
-    __syncthreads();      // ... for every thread; and chunk gi-1 has been consumed by all warps
-    issue_group(gi + 2);  // refills the stage consumed at gi-1
-    const int item = gi / C::NCH, c = gi - item * C::NCH;
-    const double* A = As + (gi % C::NSTAGE) * C::KC * C::LDA + wm * 32 + g;
-    const double* B;
-    int ldb;
-    if (c < C::NCH_D) {
-      B = Xs + (item & 1) * C::NT * C::LDX + (wn * 32 + g) * C::LDX + c * C::KC + t;
-      ldb = C::LDX;
-    } else {
-      B = Fs + (wn * 32 + g) * C::LDF + (c - C::NCH_D) * C::KC + t;
-      ldb = C::LDF;
+  int g = 0;
+  for (int item = 0; item < my; ++item) {
+    const int buf = item & 1;
+    mbar_wait(&x_full[buf], (item >> 1) & 1);
+    for (int c = 0; c < C::NCH; ++c, ++g) {
+      const int st = g % C::NSTAGE;
+      if (C::K1 && c == C::NCH0) mbar_wait(f_full, item & 1);
+      mbar_wait(&a_full[st], (g / C::NSTAGE) & 1);
+      const double* A = As + st * C::KC * C::LDA + wr * (C::TM * 8) + gq;
+      const double* B;
+      int ldb;
+      if (c < C::NCH0) {
+        B = Xs + buf * C::NT * C::LDX + (wc * (C::TN * 8) + gq) * C::LDX + c * C::KC + t;
+        ldb = C::LDX;
+      } else {
+        B = Fs + (wc * (C::TN * 8) + gq) * C::LDF + (c - C::NCH0) * C::KC + t;
+        ldb = C::LDF;
+      }
+#pragma unroll 4
+      for (int kk = 0; kk < C::KC / 4; ++kk) {
+        double a[C::TM], b[C::TN];
+#pragma unroll
+        for (int i = 0; i < C::TM; ++i) a[i] = A[(kk * 4 + t) * C::LDA + i * 8];
+#pragma unroll
+        for (int j = 0; j < C::TN; ++j) b[j] = B[j * 8 * ldb + kk * 4];
+#pragma unroll
+        for (int i = 0; i < C::TM; ++i)
+#pragma unroll
+          for (int j = 0; j < C::TN; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&a_empty[st]);
+        if (c == C::NCH0 - 1) mbar_arrive(&x_empty[buf]);
+        if (C::K1 && c == C::NCH - 1) mbar_arrive(f_empty);
+      }
     }
+    // ---- epilogue of the item
+    const GTask& tk = tasks[(first + item) / ntiles];
+    const int tile = (first + item) % ntiles, ncols = item_cols(item);
+    double* O;
+    int64_t ldo;
+    if (DOWN) { O = p.Y + tk.c + (int64_t)tile * C::NT * p.ldy; ldo = p.ldy; }
+    else { O = p.Z + tk.c * (int64_t)nrhs + (int64_t)tile * C::NT * R; ldo = R; }
 #pragma unroll
-    for (int kk = 0; kk < C::KC / 4; ++kk) {
-      double a[4], b[4];
+    for (int j = 0; j < C::TN; ++j) {
+      const int col = wc * (C::TN * 8) + j * 8 + 2 * t;
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = A[(kk * 4 + t) * C::LDA + i * 8];
+      for (int i = 0; i < C::TM; ++i) {
+        const int row = wr * (C::TM * 8) + i * 8 + gq;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = B[j * 8 * ldb + kk * 4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
-    }
-    if (c == C::NCH - 1) {  // epilogue of the item: Y = alpha*acc + beta*Y (beta == 0 never reads Y)
-      const GTask& tk = tasks[(first + item) / ntiles];
-      const int tile = (first + item) % ntiles;
-      const int ncols = item_cols(item);
-      double* Y = p.Y + tk.c + (int64_t)tile * C::NT * p.ldy;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int col = wn * 32 + j * 8 + 2 * t;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = wm * 32 + i * 8 + g;
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            if (col + e < ncols) {
-              double* dst = Y + (int64_t)(col + e) * p.ldy + row;
-              double v = p.alpha * acc[i][j][e];
-              if (p.beta != 0.0) v += p.beta * (*dst);
-              *dst = v;
+        for (int e = 0; e < 2; ++e) {
+          if (col + e < ncols) {
+            double* dst = O + (int64_t)(col + e) * ldo + row;
+            double v = acc[i][j][e];
+            if (DOWN) {
+              v *= p.alpha;
+              if (p.beta != 0.0) v += p.beta * (*dst);  // beta == 0 never reads Y (matmul.jl:13)
             }
-            acc[i][j][e] = 0.0;
+            *dst = v;
           }
+          acc[i][j][e] = 0.0;
         }
       }
     }
   }
-  cp_async_wait<0>();
-}
-
-// ================================================================= leaf up ===
-// Z'[NT x R] = X'[NT x M] * V[M x R] for one (leaf, column tile) item at a time; X resident
-// (double buffered across items), V streamed in contiguous chunks of VC columns.  Each chunk
-// yields a complete NT x VC slab of Z' = (NT/8)*(VC/8) = 8 DMMA tiles, one per warp, K = M.
-template <int M, int R>
-__global__ void __launch_bounds__(256, 1)
-leaf_up_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p) {
-  using C = LeafCfg<M, R>;
-  constexpr int S = C::UP_STAGES;
-  extern __shared__ __align__(16) double smem[];
-  double* Xs = smem;                     // [2][NT][LDX]
-  double* Vs = Xs + 2 * C::NT * C::LDX;  // [S][VC][LDA]
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int g = lane >> 2, t = lane & 3;
-  constexpr int JT = C::NT / 8;          // column tiles of X per chunk
-  const int jt = warp % JT, vt = warp / JT;  // this warp's tile: X columns jt*8.., V columns vt*8.. of the chunk
-  const int nitems = ntasks * ntiles;
-  const int first = (int)(((int64_t)blockIdx.x * nitems) / gridDim.x);
-  const int last = (int)(((int64_t)(blockIdx.x + 1) * nitems) / gridDim.x);
-  const int my = last - first;
-  if (my <= 0) return;
-  const int G = my * C::NVC;
-  const int nrhs = p.nrhs;
-
-  auto item_cols = [&](int item) { return min(C::NT, nrhs - ((first + item) % ntiles) * C::NT); };
-  auto load_x = [&](int item) {
-    const GTask& tk = tasks[(first + item) / ntiles];
-    const int tile = (first + item) % ntiles;
-    const double* src = p.X + tk.b0 + (int64_t)tile * C::NT * p.ldx;
-    copy_block_async<256>(Xs + (item & 1) * C::NT * C::LDX, C::LDX, src, p.ldx, M, item_cols(item), tid);
-  };
-  auto issue_group = [&](int gi) {
-    if (gi < G) {
-      const int item = gi / C::NVC, c = gi - item * C::NVC;
-      const GTask& tk = tasks[(first + item) / ntiles];
-      copy_block_async<256>(Vs + (gi % S) * C::VC * C::LDA, C::LDA, p.pool + tk.a0 + (int64_t)c * C::VC * M, M, M, C::VC, tid);
-    }
-    cp_async_commit();
-  };
-
-  load_x(0);
-  cp_async_commit();
-#pragma unroll
-  for (int s = 0; s < S - 1; ++s) issue_group(s);
-
-  for (int gi = 0; gi < G; ++gi) {
-    cp_async_wait<S - 2>();
-    __syncthreads();
-    const int item = gi / C::NVC, c = gi - item * C::NVC;
-    // Prefetch the next item's X block at the first chunk of this item: the buffer it overwrites
-    // was last read by item-1, which every warp left before the barrier above.  It joins the
-    // cp.async group committed by issue_group() below, i.e. group gi+S-1 <= (item+1)*NVC, so it
-    // has landed when item+1 starts (UP_STAGES - 1 <= NVC).
-    if (c == 0 && item + 1 < my) load_x(item + 1);
-    issue_group(gi + S - 1);
-    const double* A = Xs + (item & 1) * C::NT * C::LDX + (jt * 8 + g) * C::LDX + t;   // X'(j, k)
-    const double* B = Vs + (gi % S) * C::VC * C::LDA + (vt * 8 + g) * C::LDA + t;     // V(k, n)
-    double c0[2] = {0.0, 0.0}, c1[2] = {0.0, 0.0};  // two independent chains over K
-#pragma unroll 8
-    for (int kk = 0; kk < M / 4; kk += 2) {
-      mma_m8n8k4(c0[0], c0[1], A[kk * 4], B[kk * 4]);
-      mma_m8n8k4(c1[0], c1[1], A[kk * 4 + 4], B[kk * 4 + 4]);
-    }
-    // Z'(j, n) -> Z(n, j): lane holds n = 2t, 2t+1 (adjacent rows of Z) for column j = g
-    const GTask& tk = tasks[(first + item) / ntiles];
-    const int tile = (first + item) % ntiles;
-    const int col = jt * 8 + g;
-    if (col < item_cols(item)) {
-      double* Z = p.Z + tk.c * (int64_t)nrhs + (int64_t)(tile * C::NT + col) * R + c * C::VC + vt * 8 + 2 * t;
-      *reinterpret_cast<double2*>(Z) = make_double2(c0[0] + c1[0], c0[1] + c1[1]);
-    }
-  }
-  cp_async_wait<0>();
 }
 
 // =================================================================== merge ===
 // Z[R x NT] = W1'[R x R] Z1 + W2'[R x R] Z2 for one (node, column tile); 128 threads,
-// warp w owns columns w*16 .. w*16+15 of the tile (R/8 x 2 DMMA tiles).
+// warp w owns columns w*NT/4 .. of the tile (R/8 x NT/32 DMMA tiles).
 template <int R>
 struct NodeCfg {
-  static constexpr int NT = 64;
+  static constexpr int NT = R >= 64 ? 32 : 64;
+  static constexpr int TN = NT / 32;  // column tiles per warp
   static constexpr int LD = R + 4;
   static constexpr size_t MERGE_SMEM = sizeof(double) * (2 * R * LD + 2 * NT * LD);
-  static constexpr size_t TRANS_SMEM = sizeof(double) * (4 * R * LD + 3 * NT * LD);
+  static constexpr size_t TRANS_SMEM = sizeof(double) * (2 * R * LD + 2 * NT * LD);
 };
+
+// acc += op(A) * B over K = R for a warp's R x (8*TN) slab.  A "T": A(i,k) at As[i*LD + k]; "N": As[k*LD + i].
+template <int R, bool TRANS_A>
+__device__ __forceinline__ void node_mma(double (&acc)[R / 8][NodeCfg<R>::TN][2], const double* As, const double* Bs, int g, int t) {
+  using C = NodeCfg<R>;
+#pragma unroll
+  for (int kk = 0; kk < R / 4; ++kk) {
+    double b[C::TN];
+#pragma unroll
+    for (int j = 0; j < C::TN; ++j) b[j] = Bs[(j * 8 + g) * C::LD + kk * 4 + t];
+#pragma unroll
+    for (int i = 0; i < R / 8; ++i) {
+      const double a = TRANS_A ? As[(i * 8 + g) * C::LD + kk * 4 + t] : As[(kk * 4 + t) * C::LD + i * 8 + g];
+#pragma unroll
+      for (int j = 0; j < C::TN; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a, b[j]);
+    }
+  }
+}
+
+template <int R>
+__device__ __forceinline__ void node_store(const double (&acc)[R / 8][NodeCfg<R>::TN][2], double* O, int col0, int ncols, int g, int t) {
+  using C = NodeCfg<R>;
+#pragma unroll
+  for (int j = 0; j < C::TN; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = col0 + j * 8 + 2 * t + e;
+      if (col < ncols) {
+#pragma unroll
+        for (int i = 0; i < R / 8; ++i) O[(int64_t)col * R + i * 8 + g] = acc[i][j][e];
+      }
+    }
+}
 
 template <int R>
 __global__ void __launch_bounds__(128)
@@ -285,112 +325,65 @@ merge_kernel(const GTask* __restrict__ tasks, CallParams p) {
   const int tile = blockIdx.y, nrhs = p.nrhs;
   const int ncols = min(C::NT, nrhs - tile * C::NT);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int64_t toff = (int64_t)tile * C::NT * R;
 
   copy_block_async<128>(Ws, C::LD, p.pool + tk.a0, R, R, R, tid);
   copy_block_async<128>(Ws + R * C::LD, C::LD, p.pool + tk.a1, R, R, R, tid);
-  copy_block_async<128>(Zs, C::LD, p.Z + tk.b0 * (int64_t)nrhs + (int64_t)tile * C::NT * R, R, R, ncols, tid);
-  copy_block_async<128>(Zs + C::NT * C::LD, C::LD, p.Z + tk.b1 * (int64_t)nrhs + (int64_t)tile * C::NT * R, R, R, ncols, tid);
+  copy_block_async<128>(Zs, C::LD, p.Z + tk.b0 * (int64_t)nrhs + toff, R, R, ncols, tid);
+  copy_block_async<128>(Zs + C::NT * C::LD, C::LD, p.Z + tk.b1 * (int64_t)nrhs + toff, R, R, ncols, tid);
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
 
-  double acc[R / 8][2][2];
+  double acc[R / 8][C::TN][2];
 #pragma unroll
   for (int i = 0; i < R / 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-#pragma unroll
-  for (int s = 0; s < 2; ++s) {
-    const double* A = Ws + s * R * C::LD + g * C::LD + t;
-    const double* B = Zs + s * C::NT * C::LD + (warp * 16 + g) * C::LD + t;
-#pragma unroll
-    for (int kk = 0; kk < R / 4; ++kk) {
-      double b[2] = {B[kk * 4], B[8 * C::LD + kk * 4]};
-#pragma unroll
-      for (int i = 0; i < R / 8; ++i) {
-        const double a = A[i * 8 * C::LD + kk * 4];
-        mma_m8n8k4(acc[i][0][0], acc[i][0][1], a, b[0]);
-        mma_m8n8k4(acc[i][1][0], acc[i][1][1], a, b[1]);
-      }
-    }
-  }
-  double* Z = p.Z + tk.c * (int64_t)nrhs + (int64_t)tile * C::NT * R;
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = warp * 16 + j * 8 + 2 * t + e;
-      if (col < ncols) {
-#pragma unroll
-        for (int i = 0; i < R / 8; ++i) Z[(int64_t)col * R + i * 8 + g] = acc[i][j][e];
-      }
-    }
+    for (int j = 0; j < C::TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int col0 = warp * (C::NT / 4);
+  node_mma<R, true>(acc, Ws, Zs + col0 * C::LD, g, t);
+  node_mma<R, true>(acc, Ws + R * C::LD, Zs + (C::NT + col0) * C::LD, g, t);
+  node_store<R>(acc, p.Z + tk.c * (int64_t)nrhs + toff, col0, ncols, g, t);
 }
 
 // =============================================================== translate ===
-// For one parent and column tile: F1 = B12 Z2 (+ R1 F), F2 = B21 Z1 (+ R2 F).  Tasks come in
-// (left child, right child) pairs; 256 threads, warps 0-3 -> F1, warps 4-7 -> F2.
+// One task = one child: F_c[R x NT] = B[R x R] Z_sibling (+ R_c[R x R] F_parent); one CTA per
+// (task, column tile), 128 threads.
 template <int R>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 translate_kernel(const GTask* __restrict__ tasks, CallParams p) {
   using C = NodeCfg<R>;
   extern __shared__ __align__(16) double smem[];
-  double* Bs = smem;                   // [2][R][LD]  B12, B21   A(i,k) at [k*LD + i]  ("N" operand)
-  double* Rs = Bs + 2 * R * C::LD;     // [2][R][LD]  R1, R2
-  double* Zs = Rs + 2 * R * C::LD;     // [2][NT][LD] Z of the sibling of child 0 / child 1
-  double* Fs = Zs + 2 * C::NT * C::LD; // [NT][LD]    F of the parent
-  const GTask t0 = tasks[2 * blockIdx.x], t1 = tasks[2 * blockIdx.x + 1];
+  double* Bs = smem;                   // [R][LD]  B12 or B21   A(i,k) at [k*LD + i]  ("N" operand)
+  double* Rs = Bs + R * C::LD;         // [R][LD]  R of the child
+  double* Zs = Rs + R * C::LD;         // [NT][LD] Z of the sibling
+  double* Fs = Zs + C::NT * C::LD;     // [NT][LD] F of the parent
+  const GTask tk = tasks[blockIdx.x];
   const int tile = blockIdx.y, nrhs = p.nrhs;
   const int ncols = min(C::NT, nrhs - tile * C::NT);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const bool has_f = t0.K1 > 0;
+  const bool has_f = tk.K1 > 0;
   const int64_t toff = (int64_t)tile * C::NT * R;
 
-  copy_block_async<256>(Bs, C::LD, p.pool + t0.a0, R, R, R, tid);
-  copy_block_async<256>(Bs + R * C::LD, C::LD, p.pool + t1.a0, R, R, R, tid);
-  copy_block_async<256>(Zs, C::LD, p.Z + t0.b0 * (int64_t)nrhs + toff, R, R, ncols, tid);
-  copy_block_async<256>(Zs + C::NT * C::LD, C::LD, p.Z + t1.b0 * (int64_t)nrhs + toff, R, R, ncols, tid);
+  copy_block_async<128>(Bs, C::LD, p.pool + tk.a0, R, R, R, tid);
+  copy_block_async<128>(Zs, C::LD, p.Z + tk.b0 * (int64_t)nrhs + toff, R, R, ncols, tid);
   if (has_f) {
-    copy_block_async<256>(Rs, C::LD, p.pool + t0.a1, R, R, R, tid);
-    copy_block_async<256>(Rs + R * C::LD, C::LD, p.pool + t1.a1, R, R, R, tid);
-    copy_block_async<256>(Fs, C::LD, p.F + t0.b1 * (int64_t)nrhs + toff, R, R, ncols, tid);
+    copy_block_async<128>(Rs, C::LD, p.pool + tk.a1, R, R, R, tid);
+    copy_block_async<128>(Fs, C::LD, p.F + tk.b1 * (int64_t)nrhs + toff, R, R, ncols, tid);
   }
   cp_async_commit();
   cp_async_wait<0>();
   __syncthreads();
 
-  const int child = warp >> 2, w = warp & 3;
-  double acc[R / 8][2][2];
+  double acc[R / 8][C::TN][2];
 #pragma unroll
   for (int i = 0; i < R / 8; ++i)
 #pragma unroll
-    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  const int nsrc = has_f ? 2 : 1;
-  for (int s = 0; s < nsrc; ++s) {
-    const double* A = (s ? Rs : Bs) + child * R * C::LD + g;
-    const double* B = (s ? Fs : Zs + child * C::NT * C::LD) + (w * 16 + g) * C::LD + t;
-#pragma unroll
-    for (int kk = 0; kk < R / 4; ++kk) {
-      double b[2] = {B[kk * 4], B[8 * C::LD + kk * 4]};
-#pragma unroll
-      for (int i = 0; i < R / 8; ++i) {
-        const double a = A[(kk * 4 + t) * C::LD + i * 8];
-        mma_m8n8k4(acc[i][0][0], acc[i][0][1], a, b[0]);
-        mma_m8n8k4(acc[i][1][0], acc[i][1][1], a, b[1]);
-      }
-    }
-  }
-  double* F = p.F + (child ? t1.c : t0.c) * (int64_t)nrhs + toff;
-#pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = w * 16 + j * 8 + 2 * t + e;
-      if (col < ncols) {
-#pragma unroll
-        for (int i = 0; i < R / 8; ++i) F[(int64_t)col * R + i * 8 + g] = acc[i][j][e];
-      }
-    }
+    for (int j = 0; j < C::TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int col0 = warp * (C::NT / 4);
+  node_mma<R, false>(acc, Bs, Zs + col0 * C::LD, g, t);
+  if (has_f) node_mma<R, false>(acc, Rs, Fs + col0 * C::LD, g, t);
+  node_store<R>(acc, p.F + tk.c * (int64_t)nrhs + toff, col0, ncols, g, t);
 }
 
 // ================================================================ host side ===
@@ -408,17 +401,19 @@ struct FastState {
 
 template <int M, int R>
 static int launch_leaf(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st, bool down) {
-  using C = LeafCfg<M, R>;
   FastState* fs = (FastState*)H->fast_state;
-  const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
-  const int nitems = (int)ph.ntasks * ntiles;
-  const int grid = std::min(nitems, fs->num_sms);
   if (down) {
-    if (int rc = fs->configure((const void*)leaf_down_kernel<M, R>, C::DOWN_SMEM)) return rc;
-    leaf_down_kernel<M, R><<<grid, 256, C::DOWN_SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
+    using C = StreamCfg<M, R, true>;
+    const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
+    const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
+    if (int rc = fs->configure((const void*)stream_leaf_kernel<M, R, true>, C::SMEM)) return rc;
+    stream_leaf_kernel<M, R, true><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
   } else {
-    if (int rc = fs->configure((const void*)leaf_up_kernel<M, R>, C::UP_SMEM)) return rc;
-    leaf_up_kernel<M, R><<<grid, 256, C::UP_SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
+    using C = StreamCfg<M, R, false>;
+    const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
+    const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
+    if (int rc = fs->configure((const void*)stream_leaf_kernel<M, R, false>, C::SMEM)) return rc;
+    stream_leaf_kernel<M, R, false><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
   }
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
@@ -435,7 +430,7 @@ static int launch_node(hssb_matrix* H, const Phase& ph, const CallParams& cp, cu
     merge_kernel<R><<<dim3((unsigned)ph.ntasks, (unsigned)ntiles), 128, C::MERGE_SMEM, st>>>(H->tasks_dev + ph.task0, cp);
   } else {
     if (int rc = fs->configure((const void*)translate_kernel<R>, C::TRANS_SMEM)) return rc;
-    translate_kernel<R><<<dim3((unsigned)(ph.ntasks / 2), (unsigned)ntiles), 256, C::TRANS_SMEM, st>>>(H->tasks_dev + ph.task0, cp);
+    translate_kernel<R><<<dim3((unsigned)ph.ntasks, (unsigned)ntiles), 128, C::TRANS_SMEM, st>>>(H->tasks_dev + ph.task0, cp);
   }
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
@@ -457,17 +452,15 @@ static void plan_fast_phases(hssb_matrix* H) {
     for (int64_t i = 0; i < ph.ntasks && ok; ++i) {
       const GTask& g = tk[i];
       switch (ph.kind) {
-        case PH_LEAF_UP: ok = g.M == r && g.K0 == m && g.lda0 == m && g.ldc == r && g.a0 >= 0; break;
+        case PH_LEAF_UP: ok = g.M == r && g.K0 == m && g.lda0 == r && g.ta0 == 0 && g.ldc == r && g.a0 >= 0; break;
         case PH_MERGE: ok = g.M == r && g.K0 == r && g.K1 == r && g.lda0 == r && g.lda1 == r && g.ldb0 == r && g.ldb1 == r && g.ldc == r; break;
         case PH_TRANSLATE:
           ok = g.M == r && g.K0 == r && (g.K1 == r || g.K1 == 0) && g.lda0 == r && g.ldb0 == r && g.ldc == r && (g.K1 == 0 || (g.lda1 == r && g.ldb1 == r));
-          if (ok && (i & 1)) ok = g.b1 == tk[i - 1].b1 && g.K1 == tk[i - 1].K1 && g.sb1 == tk[i - 1].sb1;  // sibling pair of one parent
           break;
         case PH_LEAF_DOWN: ok = g.M == m && g.K0 == m && g.K1 == r && g.lda0 == m && g.lda1 == m && g.ldb1 == r && g.a0 >= 0 && g.a1 >= 0; break;
         default: ok = false;
       }
     }
-    if (ph.kind == PH_TRANSLATE && (ph.ntasks & 1)) ok = false;
     if (!ok) continue;
     ph.fast = ph.kind == PH_LEAF_UP ? FAST_LEAF_UP : ph.kind == PH_MERGE ? FAST_MERGE : ph.kind == PH_TRANSLATE ? FAST_TRANSLATE : FAST_LEAF_DOWN;
   }

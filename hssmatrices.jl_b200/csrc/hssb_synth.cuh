@@ -34,8 +34,9 @@ constexpr int KIND_X = 7;
 struct SynthBlock {
   int64_t off;   // pool offset (doubles)
   uint64_t key;
-  int32_t rows, cols, ld;
-  double c;      // IH4_SCALE * scale
+  int32_t rows, cols, ld;  // as stored
+  int32_t transposed;      // 1: stored(i, j) = logical(j, i), the logical block being cols x rows
+  double c;                // IH4_SCALE * scale
 };
 
 // One CTA per block descriptor (grid-stride), threads sweep the elements.
@@ -45,7 +46,8 @@ __global__ void synth_fill_kernel(const SynthBlock* __restrict__ blocks, int64_t
     const int64_t total = (int64_t)sb.rows * sb.cols;
     for (int64_t e = threadIdx.x; e < total; e += blockDim.x) {
       const int64_t j = e / sb.rows, i = e - j * sb.rows;
-      pool[sb.off + j * sb.ld + i] = synth_value(sb.key, (uint64_t)e, sb.c);
+      const int64_t idx = sb.transposed ? i * sb.cols + j : e;
+      pool[sb.off + j * sb.ld + i] = synth_value(sb.key, (uint64_t)idx, sb.c);
     }
   }
 }
