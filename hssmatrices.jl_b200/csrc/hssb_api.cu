@@ -200,8 +200,12 @@ static void layout_pool(hssb_matrix* H) {
     int64_t rows, cols;
     block_shape(nodes, t, kind, rows, cols);
     t.rows[kind] = rows; t.cols[kind] = cols;
-    if (rows == 0 || cols == 0) { t.off[kind] = -1; t.ld[kind] = (int32_t)std::max<int64_t>(round_up(rows, 2), 2); return; }
-    t.ld[kind] = (int32_t)round_up(rows, 2);
+    // Uniform trees served by the fixed-shape kernels store every block with the +4 padded leading
+    // dimension of its shared-memory image, so that a block (or a run of its columns) is ONE
+    // contiguous TMA bulk copy that lands bank-conflict free.
+    const int64_t ldp = H->padded ? rows + 4 : round_up(rows, 2);
+    if (rows == 0 || cols == 0) { t.off[kind] = -1; t.ld[kind] = (int32_t)std::max<int64_t>(ldp, 2); return; }
+    t.ld[kind] = (int32_t)ldp;
     t.off[kind] = off;
     off += round_up((int64_t)t.ld[kind] * cols, 16);
     gen += rows * cols;
@@ -228,16 +232,17 @@ static void layout_workspace(hssb_matrix* H) {
   if (P > 1) {
     int64_t slot = 0;
     for (auto& t : nodes)
-      if (t.depth == p) slot = std::max<int64_t>(slot, round_up(t.kw, 2));
+      if (t.depth == p) slot = std::max<int64_t>(slot, H->padded ? t.kw + 4 : round_up(t.kw, 2));
     H->xchg_zoff = 0;
     H->xchg_slot_rows = slot;
     for (auto& t : nodes)
-      if (t.depth == p) { t.zoff = zo; t.ldz = (int32_t)std::max<int64_t>(round_up(t.kw, 2), 2); zo += slot; }
+      if (t.depth == p) { t.zoff = zo; t.ldz = (int32_t)std::max<int64_t>(H->padded ? t.kw + 4 : round_up(t.kw, 2), 2); zo += slot; }
   }
   for (size_t i = 1; i < nodes.size(); ++i) {  // BFS order keeps siblings adjacent
     Node& t = nodes[i];
-    if (t.zoff < 0) { t.zoff = zo; t.ldz = (int32_t)std::max<int64_t>(round_up(t.kw, 2), 2); zo += round_up(t.kw, 2); }
-    t.foff = fo; t.ldf = (int32_t)std::max<int64_t>(round_up(t.kr, 2), 2); fo += round_up(t.kr, 2);
+    const int64_t lz = H->padded ? t.kw + 4 : round_up(t.kw, 2), lf = H->padded ? t.kr + 4 : round_up(t.kr, 2);
+    if (t.zoff < 0) { t.zoff = zo; t.ldz = (int32_t)std::max<int64_t>(lz, 2); zo += lz; }
+    t.foff = fo; t.ldf = (int32_t)std::max<int64_t>(lf, 2); fo += lf;
   }
   H->z_rows = std::max<int64_t>(zo, 2);
   H->f_rows = std::max<int64_t>(fo, 2);
@@ -401,10 +406,11 @@ static int plan_matrix(hssb_matrix* H) {
     }
     H->max_rank = std::max(H->max_rank, std::max(t.kr, t.kw));
   }
+  detect_uniform(H);
+  H->padded = H->uniform && fast_shape_supported(H->uni_m, H->uni_r);
   layout_pool(H);
   layout_workspace(H);
   build_plan(H);
-  detect_uniform(H);
   plan_fast_phases(H);
 
   return HSSB_OK;

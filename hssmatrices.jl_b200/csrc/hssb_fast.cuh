@@ -166,10 +166,11 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
       const GTask& tk = tasks[(first + item) / ntiles];
       const int tile = (first + item) % ntiles, nc = item_cols(item);
       mbar_wait(f_empty, (item & 1) ^ 1);
-      if (lane == 0) mbar_expect_tx(f_full, (uint32_t)(nc * C::K1 * 8));
-      __syncwarp();
-      const double* src = p.F + tk.b1 * (int64_t)nrhs + (int64_t)tile * C::NT * C::K1;
-      for (int c = lane; c < nc; c += 32) bulk_g2s(Fs + c * C::LDF, src + (int64_t)c * C::K1, C::K1 * 8, f_full);
+      if (lane == 0) {  // the F workspace already carries the padded leading dimension: one copy per tile
+        const uint32_t bytes = (uint32_t)(nc * C::LDF * 8);
+        mbar_expect_tx(f_full, bytes);
+        bulk_g2s(Fs, p.F + tk.b1 * (int64_t)nrhs + (int64_t)tile * C::NT * C::LDF, bytes, f_full);
+      }
     };
     load_x(0);
     int g = 0;
@@ -178,11 +179,13 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
       for (int c = 0; c < C::NCH; ++c, ++g) {
         const int st = g % C::NSTAGE;
         mbar_wait(&a_empty[st], ((g / C::NSTAGE) & 1) ^ 1);
-        if (lane == 0) mbar_expect_tx(&a_full[st], (uint32_t)(C::KC * C::MO * 8));
+        if (lane == 0) {  // KC columns of the padded pool image = one contiguous copy
+          constexpr uint32_t bytes = C::KC * C::LDA * 8;
+          const double* src = p.pool + (c < C::NCH0 ? tk.a0 + (int64_t)c * C::KC * C::LDA : tk.a1 + (int64_t)(c - C::NCH0) * C::KC * C::LDA);
+          mbar_expect_tx(&a_full[st], bytes);
+          bulk_g2s(As + st * C::KC * C::LDA, src, bytes, &a_full[st]);
+        }
         __syncwarp();
-        const double* src = p.pool + (c < C::NCH0 ? tk.a0 + (int64_t)c * C::KC * C::MO : tk.a1 + (int64_t)(c - C::NCH0) * C::KC * C::MO);
-        double* dst = As + st * C::KC * C::LDA;
-        for (int col = lane; col < C::KC; col += 32) bulk_g2s(dst + col * C::LDA, src + (int64_t)col * C::MO, C::MO * 8, &a_full[st]);
         if (c == C::CX) {
           load_f(item);
           if (item + 1 < my) load_x(item + 1);
@@ -244,7 +247,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
     double* O;
     int64_t ldo;
     if (DOWN) { O = p.Y + tk.c + (int64_t)tile * C::NT * p.ldy; ldo = p.ldy; }
-    else { O = p.Z + tk.c * (int64_t)nrhs + (int64_t)tile * C::NT * R; ldo = R; }
+    else { O = p.Z + tk.c * (int64_t)nrhs + (int64_t)tile * C::NT * (R + 4); ldo = R + 4; }
 #pragma unroll
     for (int j = 0; j < C::TN; ++j) {
       const int col = wc * (C::TN * 8) + j * 8 + 2 * t;
@@ -277,8 +280,8 @@ struct NodeCfg {
   static constexpr int NT = R >= 64 ? 32 : 64;
   static constexpr int TN = NT / 32;  // column tiles per warp
   static constexpr int LD = R + 4;
-  static constexpr size_t MERGE_SMEM = sizeof(double) * (2 * R * LD + 2 * NT * LD);
-  static constexpr size_t TRANS_SMEM = sizeof(double) * (2 * R * LD + 2 * NT * LD);
+  static constexpr size_t MERGE_SMEM = 128 + sizeof(double) * (2 * R * LD + 2 * NT * LD);
+  static constexpr size_t TRANS_SMEM = 128 + sizeof(double) * (2 * R * LD + 2 * NT * LD);
 };
 
 // acc += op(A) * B over K = R for a warp's R x (8*TN) slab.  A "T": A(i,k) at As[i*LD + k]; "N": As[k*LD + i].
@@ -309,7 +312,7 @@ __device__ __forceinline__ void node_store(const double (&acc)[R / 8][NodeCfg<R>
       const int col = col0 + j * 8 + 2 * t + e;
       if (col < ncols) {
 #pragma unroll
-        for (int i = 0; i < R / 8; ++i) O[(int64_t)col * R + i * 8 + g] = acc[i][j][e];
+        for (int i = 0; i < R / 8; ++i) O[(int64_t)col * C::LD + i * 8 + g] = acc[i][j][e];
       }
     }
 }
@@ -318,22 +321,29 @@ template <int R>
 __global__ void __launch_bounds__(128)
 merge_kernel(const GTask* __restrict__ tasks, CallParams p) {
   using C = NodeCfg<R>;
-  extern __shared__ __align__(16) double smem[];
-  double* Ws = smem;                   // [2][R][LD]   W(k, i) at Ws[i*LD + k]  ("T" operand)
-  double* Zs = Ws + 2 * R * C::LD;     // [2][NT][LD]
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* Ws = reinterpret_cast<double*>(smem_raw + 128);  // [2][R][LD]   W(k, i) at Ws[i*LD + k]  ("T" operand)
+  double* Zs = Ws + 2 * R * C::LD;                         // [2][NT][LD]
   const GTask tk = tasks[blockIdx.x];
   const int tile = blockIdx.y, nrhs = p.nrhs;
   const int ncols = min(C::NT, nrhs - tile * C::NT);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int64_t toff = (int64_t)tile * C::NT * R;
+  const int64_t toff = (int64_t)tile * C::NT * C::LD;
 
-  copy_block_async<128>(Ws, C::LD, p.pool + tk.a0, R, R, R, tid);
-  copy_block_async<128>(Ws + R * C::LD, C::LD, p.pool + tk.a1, R, R, R, tid);
-  copy_block_async<128>(Zs, C::LD, p.Z + tk.b0 * (int64_t)nrhs + toff, R, R, ncols, tid);
-  copy_block_async<128>(Zs + C::NT * C::LD, C::LD, p.Z + tk.b1 * (int64_t)nrhs + toff, R, R, ncols, tid);
-  cp_async_commit();
-  cp_async_wait<0>();
-  __syncthreads();
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    constexpr uint32_t wb = R * C::LD * 8;
+    const uint32_t zb = (uint32_t)(ncols * C::LD * 8);
+    mbar_expect_tx(bar, 2 * wb + 2 * zb);
+    bulk_g2s(Ws, p.pool + tk.a0, wb, bar);
+    bulk_g2s(Ws + R * C::LD, p.pool + tk.a1, wb, bar);
+    bulk_g2s(Zs, p.Z + tk.b0 * (int64_t)nrhs + toff, zb, bar);
+    bulk_g2s(Zs + C::NT * C::LD, p.Z + tk.b1 * (int64_t)nrhs + toff, zb, bar);
+  }
+  __syncthreads();  // the barrier is initialised before anyone polls it
+  mbar_wait(bar, 0);
 
   double acc[R / 8][C::TN][2];
 #pragma unroll
@@ -353,8 +363,9 @@ template <int R>
 __global__ void __launch_bounds__(128)
 translate_kernel(const GTask* __restrict__ tasks, CallParams p) {
   using C = NodeCfg<R>;
-  extern __shared__ __align__(16) double smem[];
-  double* Bs = smem;                   // [R][LD]  B12 or B21   A(i,k) at [k*LD + i]  ("N" operand)
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* Bs = reinterpret_cast<double*>(smem_raw + 128);  // [R][LD]  B12 or B21   A(i,k) at [k*LD + i]  ("N" operand)
   double* Rs = Bs + R * C::LD;         // [R][LD]  R of the child
   double* Zs = Rs + R * C::LD;         // [NT][LD] Z of the sibling
   double* Fs = Zs + C::NT * C::LD;     // [NT][LD] F of the parent
@@ -363,17 +374,23 @@ translate_kernel(const GTask* __restrict__ tasks, CallParams p) {
   const int ncols = min(C::NT, nrhs - tile * C::NT);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const bool has_f = tk.K1 > 0;
-  const int64_t toff = (int64_t)tile * C::NT * R;
+  const int64_t toff = (int64_t)tile * C::NT * C::LD;
 
-  copy_block_async<128>(Bs, C::LD, p.pool + tk.a0, R, R, R, tid);
-  copy_block_async<128>(Zs, C::LD, p.Z + tk.b0 * (int64_t)nrhs + toff, R, R, ncols, tid);
-  if (has_f) {
-    copy_block_async<128>(Rs, C::LD, p.pool + tk.a1, R, R, R, tid);
-    copy_block_async<128>(Fs, C::LD, p.F + tk.b1 * (int64_t)nrhs + toff, R, R, ncols, tid);
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    constexpr uint32_t gb = R * C::LD * 8;
+    const uint32_t zb = (uint32_t)(ncols * C::LD * 8);
+    mbar_expect_tx(bar, has_f ? 2 * (gb + zb) : gb + zb);
+    bulk_g2s(Bs, p.pool + tk.a0, gb, bar);
+    bulk_g2s(Zs, p.Z + tk.b0 * (int64_t)nrhs + toff, zb, bar);
+    if (has_f) {
+      bulk_g2s(Rs, p.pool + tk.a1, gb, bar);
+      bulk_g2s(Fs, p.F + tk.b1 * (int64_t)nrhs + toff, zb, bar);
+    }
   }
-  cp_async_commit();
-  cp_async_wait<0>();
   __syncthreads();
+  mbar_wait(bar, 0);
 
   double acc[R / 8][C::TN][2];
 #pragma unroll
@@ -443,7 +460,7 @@ static bool fast_shape_supported(int64_t m, int64_t r) {
 
 // Tags the phases of a uniform tree that a fixed-shape kernel can run.
 static void plan_fast_phases(hssb_matrix* H) {
-  if (!H->uniform || !fast_shape_supported(H->uni_m, H->uni_r)) return;
+  if (!H->uniform || !H->padded || !fast_shape_supported(H->uni_m, H->uni_r)) return;
   const int m = (int)H->uni_m, r = (int)H->uni_r;
   for (Phase& ph : H->phases) {
     if (ph.kind == PH_EXCHANGE || ph.ntasks == 0) continue;
@@ -452,12 +469,14 @@ static void plan_fast_phases(hssb_matrix* H) {
     for (int64_t i = 0; i < ph.ntasks && ok; ++i) {
       const GTask& g = tk[i];
       switch (ph.kind) {
-        case PH_LEAF_UP: ok = g.M == r && g.K0 == m && g.lda0 == r && g.ta0 == 0 && g.ldc == r && g.a0 >= 0; break;
-        case PH_MERGE: ok = g.M == r && g.K0 == r && g.K1 == r && g.lda0 == r && g.lda1 == r && g.ldb0 == r && g.ldb1 == r && g.ldc == r; break;
+        // the kernels rely on the padded (+4) leading dimensions of the pool and the workspaces
+        case PH_LEAF_UP: ok = g.M == r && g.K0 == m && g.lda0 == r + 4 && g.ta0 == 0 && g.ldc == r + 4 && g.a0 >= 0; break;
+        case PH_MERGE: ok = g.M == r && g.K0 == r && g.K1 == r && g.lda0 == r + 4 && g.lda1 == r + 4 && g.ldb0 == r + 4 && g.ldb1 == r + 4 && g.ldc == r + 4 && g.a0 >= 0 && g.a1 >= 0; break;
         case PH_TRANSLATE:
-          ok = g.M == r && g.K0 == r && (g.K1 == r || g.K1 == 0) && g.lda0 == r && g.ldb0 == r && g.ldc == r && (g.K1 == 0 || (g.lda1 == r && g.ldb1 == r));
+          ok = g.M == r && g.K0 == r && (g.K1 == r || g.K1 == 0) && g.lda0 == r + 4 && g.ldb0 == r + 4 && g.ldc == r + 4 && g.a0 >= 0 &&
+               (g.K1 == 0 || (g.lda1 == r + 4 && g.ldb1 == r + 4 && g.a1 >= 0));
           break;
-        case PH_LEAF_DOWN: ok = g.M == m && g.K0 == m && g.K1 == r && g.lda0 == m && g.lda1 == m && g.ldb1 == r && g.a0 >= 0 && g.a1 >= 0; break;
+        case PH_LEAF_DOWN: ok = g.M == m && g.K0 == m && g.K1 == r && g.lda0 == m + 4 && g.lda1 == m + 4 && g.ldb1 == r + 4 && g.a0 >= 0 && g.a1 >= 0; break;
         default: ok = false;
       }
     }

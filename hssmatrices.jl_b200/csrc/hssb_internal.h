@@ -126,6 +126,7 @@ struct hssb_matrix {
   int64_t m = 0, n = 0, local_m = 0, local_n = 0, local_row0 = 0, local_col0 = 0;
   int64_t depth = 0, max_leaf_m = 0, max_leaf_n = 0, max_rank = 0;
   bool uniform = false;
+  bool padded = false;  // pool / workspace blocks carry the +4 padded leading dimension (TMA-ready images)
   int64_t uni_m = 0, uni_r = 0;  // leaf size / rank when uniform
   // exchange
   int64_t xchg_zoff = -1, xchg_slot_rows = 0;  // all-gather buffer = P slots of slot_rows x nrhs
