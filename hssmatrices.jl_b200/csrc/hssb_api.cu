@@ -710,7 +710,7 @@ static void invalidate_graphs(hssb_matrix* H) {
 
 static bool same_call(const CallParams& a, const CallParams& b) {
   return a.pool == b.pool && a.X == b.X && a.Y == b.Y && a.Z == b.Z && a.F == b.F && a.ldx == b.ldx && a.ldy == b.ldy &&
-         a.nrhs == b.nrhs && a.alpha == b.alpha && a.beta == b.beta;
+         a.nrhs == b.nrhs && a.alpha == b.alpha && a.beta == b.beta && a.debug == b.debug;
 }
 
 static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
@@ -980,7 +980,7 @@ int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   CallParams cp;
   cp.pool = h->pool_dev; cp.X = dX; cp.Y = dY; cp.Z = h->z_dev; cp.F = h->f_dev;
-  cp.ldx = ldx; cp.ldy = ldy; cp.nrhs = (int32_t)nrhs; cp.alpha = alpha; cp.beta = beta;
+  cp.ldx = ldx; cp.ldy = ldy; cp.nrhs = (int32_t)nrhs; cp.alpha = alpha; cp.beta = beta; cp.debug = h->debug_mode;
   if (h->use_graph && h->n_shards == 1) return run_graph(h, cp, st);
   return run_phases(h, cp, st);
 }
@@ -1042,6 +1042,7 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
     case HSSB_OPT_USE_GRAPH: h->use_graph = value != 0; break;
     case HSSB_OPT_FUSED_LEAF: h->fused_leaf = value != 0; break;
     case HSSB_OPT_PROFILE: h->profile = value != 0; break;
+    case HSSB_OPT_DEBUG: h->debug_mode = (int)value; break;
     default: HSSB_FAIL(HSSB_ERR_ARG, "hssb_set_option: unknown option %d", opt);
   }
   if (h->device < 0) return HSSB_OK;

@@ -55,6 +55,72 @@ __global__ void __launch_bounds__(128) dmma_occupancy_kernel(double* out, int it
   if (s == 123.456) out[0] = s;
 }
 
+// The leaf-down inner loop in isolation: 32x32 warp tile (4x4 DMMA tiles), fragments from shared
+// memory with the kernel's conflict-free leading dimensions, no global traffic, no barriers.
+// variant 0: fragments reloaded every k-step (as the kernel does); 1: same with 2 k-steps of
+// fragments loaded as one 16-byte LDS per operand.
+template <int VARIANT>
+__global__ void __launch_bounds__(256, 1) dmma_loop_kernel(double* out, int iters) {
+  extern __shared__ __align__(16) double sm[];
+  constexpr int LDA = 132, LDX = 132, KC = 64;
+  double* As = sm;              // [KC][LDA]
+  double* Xs = sm + KC * LDA;   // [64][LDX]
+  for (int i = threadIdx.x; i < KC * LDA + 64 * LDX; i += blockDim.x) sm[i] = 1e-3 * (i % 7);
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int wm = warp % 4, wn = warp / 4;
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  for (int it = 0; it < iters; ++it) {
+    if (VARIANT == 0) {
+      const double* A = As + wm * 32 + g + t * LDA;
+      const double* B = Xs + (wn * 32 + g) * LDX + t;
+#pragma unroll
+      for (int kk = 0; kk < KC / 4; ++kk) {
+        double a[4], b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) a[i] = A[kk * 4 * LDA + i * 8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = B[j * 8 * LDX + kk * 4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+    } else {
+      // k permuted so that one lane needs k = 2t, 2t+1 of each group of 8: B via one LDS.128
+      const double* A = As + wm * 32 + g + 2 * t * LDA;
+      const double* B = Xs + (wn * 32 + g) * LDX + 2 * t;
+#pragma unroll
+      for (int kk = 0; kk < KC / 8; ++kk) {
+        double a0[4], a1[4];
+        double2 b[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { a0[i] = A[kk * 8 * LDA + i * 8]; a1[i] = A[(kk * 8 + 1) * LDA + i * 8]; }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const double2*>(B + j * 8 * LDX + kk * 8);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a0[i], b[j].x);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a1[i], b[j].y);
+      }
+    }
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) s += acc[i][j][0] + acc[i][j][1];
+  if (s == 123.456) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
@@ -115,6 +181,27 @@ extern "C" int hssb_measure_peak(int device, int kind, int64_t arg, double* out)
       float ms = 0;
       HSSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       const double flops = 16.0 * 512.0 * iters * (threads / 32.0) * grid;
+      if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaFree(d);
+  } else if (kind == 4 || kind == 5) {
+    // arg = CTAs per SM (1 or 2)
+    const int per_sm = arg >= 1 && arg <= 2 ? (int)arg : 1;
+    const int iters = 400, grid = prop.multiProcessorCount * per_sm;
+    const size_t smem = sizeof(double) * (64 * 132 + 64 * 132);
+    double* d = nullptr;
+    HSSB_CUDA(cudaMalloc(&d, 64));
+    HSSB_CUDA(cudaFuncSetAttribute(dmma_loop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HSSB_CUDA(cudaFuncSetAttribute(dmma_loop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int rep = 0; rep < 4; ++rep) {
+      HSSB_CUDA(cudaEventRecord(e0));
+      if (kind == 4) dmma_loop_kernel<0><<<grid, 256, smem>>>(d, iters);
+      else dmma_loop_kernel<1><<<grid, 256, smem>>>(d, iters);
+      HSSB_CUDA(cudaEventRecord(e1));
+      HSSB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      HSSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double flops = 2.0 * 128 * 64 * 64 * (double)iters * grid;  // 128x64 tile, K = 64 per iteration
       if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
     }
     cudaFree(d);

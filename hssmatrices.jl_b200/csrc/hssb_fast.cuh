@@ -18,6 +18,8 @@
 //   translate_kernel<R>            F1 = B12 Z2 + R1 F ; F2 = B21 Z1 + R2 F   one CTA per (parent, tile)
 #pragma once
 
+#include <type_traits>
+
 #include "hssb_internal.h"
 #include "hssb_mma.cuh"
 
@@ -103,15 +105,24 @@ struct StreamCfg {
   static constexpr int WC = 8 / WR;                                  // warps along right-hand sides
   static constexpr int TM = MO / WR / 8, TN = NT / WC / 8;           // DMMA tiles per warp
   static constexpr int KC = DOWN ? (M >= 256 ? 8 : 16) : (4096 / R > M ? M : 4096 / R);
-  static constexpr int NSTAGE = DOWN ? 3 : 2;
+  static constexpr int KSTEPS = KC / 4;
   static constexpr int NCH0 = K0 / KC, NCH1 = K1 / KC, NCH = NCH0 + NCH1;
   static constexpr int LDX = K0 + 4, LDF = K1 + 4, LDA = MO + 4;
-  static constexpr int CX = (NSTAGE < NCH0 - 1) ? NSTAGE : NCH0 - 1;  // chunk after which F(i) and X(i+1) are issued
   static constexpr int BAR_BYTES = 128;
-  static constexpr size_t SMEM = BAR_BYTES + sizeof(double) * (2 * NT * LDX + (K1 ? NT * LDF : 0) + NSTAGE * KC * LDA);
+  static constexpr int FIXED_BYTES = BAR_BYTES + 8 * (2 * NT * LDX + (K1 ? NT * LDF : 0));
+  static constexpr int STAGE_BYTES = 8 * KC * LDA;
+  static constexpr int FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
+  static constexpr int NSTAGE = DOWN ? (FIT > 6 ? 6 : FIT) : 2;       // as deep a ring as shared memory allows
+  // F(i) and the first slice of X(i+1) are issued after chunk CX of item i; by then every
+  // consumer has left item i-1 (the producer can be at most NSTAGE chunks ahead), so the
+  // waits on f_empty / x_empty never hold up the A ring.
+  static constexpr int CX = (NSTAGE < NCH0 - 1) ? NSTAGE : NCH0 - 1;
+  static constexpr int XPIECES = (NCH - CX) < 8 ? (NCH - CX) : 8;     // X(i+1) is spread over this many chunks
+  static constexpr int XPC = (NT + XPIECES - 1) / XPIECES;            // columns per slice
+  static constexpr size_t SMEM = FIXED_BYTES + (size_t)NSTAGE * STAGE_BYTES;
   static_assert(MO % (8 * WR) == 0 && NT % (8 * WC) == 0 && TM >= 1 && TN >= 1, "warp tiling");
-  static_assert(K0 % KC == 0 && K1 % KC == 0 && KC % 4 == 0 && NCH0 >= 1, "chunking");
-  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(K0 % KC == 0 && K1 % KC == 0 && KC % 4 == 0 && NCH0 >= 1 && NSTAGE >= 2 && XPIECES >= 1, "chunking");
+  static_assert(SMEM <= 232448 && 2 * NSTAGE + 6 <= BAR_BYTES / 8, "shared memory budget");
 };
 
 template <int M, int R, bool DOWN>
@@ -149,17 +160,25 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
 
   auto item_cols = [&](int item) { return min(C::NT, nrhs - ((first + item) % ntiles) * C::NT); };
 
+  const bool dbg_nowait = p.debug & 1, dbg_nomma = p.debug & 2, dbg_nostore = p.debug & 4;
   if (warp == 8) {
+    if (dbg_nowait) return;
     // ====================== producer warp ======================
-    auto load_x = [&](int item) {
+    // X columns keep the user's layout (one 8*K0-byte bulk copy per column, so the shared image
+    // can carry the +4 padding); slice `piece` of `npieces` is issued per call.
+    auto load_x = [&](int item, int piece, int npieces) {
       const GTask& tk = tasks[(first + item) / ntiles];
       const int tile = (first + item) % ntiles, nc = item_cols(item), buf = item & 1;
-      mbar_wait(&x_empty[buf], ((item >> 1) & 1) ^ 1);
-      if (lane == 0) mbar_expect_tx(&x_full[buf], (uint32_t)(nc * C::K0 * 8));
-      __syncwarp();
+      if (piece == 0) {
+        mbar_wait(&x_empty[buf], ((item >> 1) & 1) ^ 1);
+        if (lane == 0) mbar_expect_tx(&x_full[buf], (uint32_t)(nc * C::K0 * 8));
+        __syncwarp();
+      }
+      const int per = (C::NT + npieces - 1) / npieces;
+      const int c0 = piece * per, c1 = min(nc, c0 + per);
       const double* src = p.X + tk.b0 + (int64_t)tile * C::NT * p.ldx;
       double* dst = Xs + buf * C::NT * C::LDX;
-      for (int c = lane; c < nc; c += 32) bulk_g2s(dst + c * C::LDX, src + (int64_t)c * p.ldx, C::K0 * 8, &x_full[buf]);
+      for (int c = c0 + lane; c < c1; c += 32) bulk_g2s(dst + c * C::LDX, src + (int64_t)c * p.ldx, C::K0 * 8, &x_full[buf]);
     };
     auto load_f = [&](int item) {
       if (C::K1 == 0) return;
@@ -172,7 +191,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
         bulk_g2s(Fs, p.F + tk.b1 * (int64_t)nrhs + (int64_t)tile * C::NT * C::LDF, bytes, f_full);
       }
     };
-    load_x(0);
+    load_x(0, 0, 1);
     int g = 0;
     for (int item = 0; item < my; ++item) {
       const GTask& tk = tasks[(first + item) / ntiles];
@@ -180,22 +199,24 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
         const int st = g % C::NSTAGE;
         mbar_wait(&a_empty[st], ((g / C::NSTAGE) & 1) ^ 1);
         if (lane == 0) {  // KC columns of the padded pool image = one contiguous copy
-          constexpr uint32_t bytes = C::KC * C::LDA * 8;
+          constexpr uint32_t bytes = C::STAGE_BYTES;
           const double* src = p.pool + (c < C::NCH0 ? tk.a0 + (int64_t)c * C::KC * C::LDA : tk.a1 + (int64_t)(c - C::NCH0) * C::KC * C::LDA);
           mbar_expect_tx(&a_full[st], bytes);
           bulk_g2s(As + st * C::KC * C::LDA, src, bytes, &a_full[st]);
         }
         __syncwarp();
-        if (c == C::CX) {
-          load_f(item);
-          if (item + 1 < my) load_x(item + 1);
-        }
+        if (c == C::CX) load_f(item);
+        if (c >= C::CX && c < C::CX + C::XPIECES && item + 1 < my) load_x(item + 1, c - C::CX, C::XPIECES);
       }
     }
     return;
   }
 
   // ====================== consumer warps ======================
+  // Each warp owns a (TM*8) x (TN*8) tile of OUT.  Per chunk it issues KSTEPS x TM x TN DMMAs.  The
+  // wait for the NEXT chunk's data is software-pipelined: the try_wait is issued two k-steps
+  // before the end of the current chunk and only checked after its DMMAs have been issued, so the
+  // ~100-cycle mbarrier round trip never sits between two DMMAs of this warp.
   const int gq = lane >> 2, t = lane & 3;
   const int wr = warp % C::WR, wc = warp / C::WR;
   double acc[C::TM][C::TN][2];
@@ -204,66 +225,123 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
 #pragma unroll
     for (int j = 0; j < C::TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-  int g = 0;
-  for (int item = 0; item < my; ++item) {
-    const int buf = item & 1;
-    mbar_wait(&x_full[buf], (item >> 1) & 1);
-    for (int c = 0; c < C::NCH; ++c, ++g) {
-      const int st = g % C::NSTAGE;
-      if (C::K1 && c == C::NCH0) mbar_wait(f_full, item & 1);
-      mbar_wait(&a_full[st], (g / C::NSTAGE) & 1);
-      const double* A = As + st * C::KC * C::LDA + wr * (C::TM * 8) + gq;
-      const double* B;
-      int ldb;
-      if (c < C::NCH0) {
-        B = Xs + buf * C::NT * C::LDX + (wc * (C::TN * 8) + gq) * C::LDX + c * C::KC + t;
-        ldb = C::LDX;
-      } else {
-        B = Fs + (wc * (C::TN * 8) + gq) * C::LDF + (c - C::NCH0) * C::KC + t;
-        ldb = C::LDF;
-      }
-#pragma unroll 4
-      for (int kk = 0; kk < C::KC / 4; ++kk) {
-        double a[C::TM], b[C::TN];
+  struct NextWait {
+    uint64_t* b0; uint32_t p0;
+    uint64_t* b1; uint32_t p1;
+  };
+  auto try_next = [&](const NextWait& w) -> bool {
+    bool ok = true;
+    if (w.b0) ok = mbar_try_wait(w.b0, w.p0);
+    if (w.b1) ok = mbar_try_wait(w.b1, w.p1) && ok;
+    return ok;
+  };
+  auto spin_next = [&](const NextWait& w) {
+    if (w.b0) mbar_wait(w.b0, w.p0);
+    if (w.b1) mbar_wait(w.b1, w.p1);
+  };
+  // One chunk: A fragments "N" from the ring stage, B fragments from X or F (ldb compile time).
+  auto chunk = [&](const double* A, const double* B, auto ldb_tag, const NextWait& nw) -> bool {
+    constexpr int LDB = decltype(ldb_tag)::value;
+    bool ok = true;
 #pragma unroll
-        for (int i = 0; i < C::TM; ++i) a[i] = A[(kk * 4 + t) * C::LDA + i * 8];
+    for (int kk = 0; kk < C::KSTEPS; ++kk) {
+      double a[C::TM], b[C::TN];
 #pragma unroll
-        for (int j = 0; j < C::TN; ++j) b[j] = B[j * 8 * ldb + kk * 4];
+      for (int i = 0; i < C::TM; ++i) a[i] = A[kk * 4 * C::LDA + i * 8];
+#pragma unroll
+      for (int j = 0; j < C::TN; ++j) b[j] = B[j * 8 * LDB + kk * 4];
+      if (kk == (C::KSTEPS >= 2 ? C::KSTEPS - 2 : 0)) ok = try_next(nw);
+      if (!dbg_nomma) {
 #pragma unroll
         for (int i = 0; i < C::TM; ++i)
 #pragma unroll
           for (int j = 0; j < C::TN; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
       }
+    }
+    return ok;
+  };
+
+  int st = 0;
+  uint32_t ph = 0;  // ring stage of the current chunk and the parity of its current use
+  if (!dbg_nowait) {
+    mbar_wait(&x_full[0], 0);
+    mbar_wait(&a_full[0], 0);
+  }
+  const double* Abase = As + wr * (C::TM * 8) + gq + t * C::LDA;
+  for (int item = 0; item < my; ++item) {
+    const int buf = item & 1;
+    const bool more = item + 1 < my;
+    // issue the loads the epilogue needs now; their latency hides behind the whole item
+    const int task_i = (first + item) / ntiles, tile = (first + item) - task_i * ntiles;
+    const int64_t out_row = tasks[task_i].c;
+    const double* Bx = Xs + buf * C::NT * C::LDX + (wc * (C::TN * 8) + gq) * C::LDX + t;
+#pragma unroll 1
+    for (int c = 0; c < C::NCH0; ++c) {
+      const int nst = (st + 1 == C::NSTAGE) ? 0 : st + 1;
+      const uint32_t nph = (st + 1 == C::NSTAGE) ? ph ^ 1 : ph;
+      NextWait nw{nullptr, 0, nullptr, 0};
+      const bool last_x = c == C::NCH0 - 1;
+      if (!dbg_nowait && (!last_x || C::K1 || more)) {
+        nw.b0 = &a_full[nst]; nw.p0 = nph;
+        if (last_x) {
+          if (C::K1) { nw.b1 = f_full; nw.p1 = item & 1; }
+          else { nw.b1 = &x_full[buf ^ 1]; nw.p1 = ((item + 1) >> 1) & 1; }
+        }
+      }
+      const bool ok = chunk(Abase + st * C::KC * C::LDA, Bx + c * C::KC, std::integral_constant<int, C::LDX>{}, nw);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&a_empty[st]);
-        if (c == C::NCH0 - 1) mbar_arrive(&x_empty[buf]);
-        if (C::K1 && c == C::NCH - 1) mbar_arrive(f_empty);
+        if (last_x) mbar_arrive(&x_empty[buf]);
+      }
+      if (!ok) spin_next(nw);
+      st = nst; ph = nph;
+    }
+    if (C::K1) {
+      const double* Bf = Fs + (wc * (C::TN * 8) + gq) * C::LDF + t;
+#pragma unroll 1
+      for (int c = 0; c < C::NCH1; ++c) {
+        const int nst = (st + 1 == C::NSTAGE) ? 0 : st + 1;
+        const uint32_t nph = (st + 1 == C::NSTAGE) ? ph ^ 1 : ph;
+        NextWait nw{nullptr, 0, nullptr, 0};
+        const bool last_f = c == C::NCH1 - 1;
+        if (!dbg_nowait && (!last_f || more)) {
+          nw.b0 = &a_full[nst]; nw.p0 = nph;
+          if (last_f) { nw.b1 = &x_full[buf ^ 1]; nw.p1 = ((item + 1) >> 1) & 1; }
+        }
+        const bool ok = chunk(Abase + st * C::KC * C::LDA, Bf + c * C::KC, std::integral_constant<int, (C::K1 ? C::LDF : 4)>{}, nw);
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&a_empty[st]);
+          if (last_f) mbar_arrive(f_empty);
+        }
+        if (!ok) spin_next(nw);
+        st = nst; ph = nph;
       }
     }
     // ---- epilogue of the item
-    const GTask& tk = tasks[(first + item) / ntiles];
-    const int tile = (first + item) % ntiles, ncols = item_cols(item);
+    const int ncols = min(C::NT, nrhs - tile * C::NT);
     double* O;
     int64_t ldo;
-    if (DOWN) { O = p.Y + tk.c + (int64_t)tile * C::NT * p.ldy; ldo = p.ldy; }
-    else { O = p.Z + tk.c * (int64_t)nrhs + (int64_t)tile * C::NT * (R + 4); ldo = R + 4; }
+    if (DOWN) { O = p.Y + out_row + (int64_t)tile * C::NT * p.ldy; ldo = p.ldy; }
+    else { O = p.Z + out_row * (int64_t)nrhs + (int64_t)tile * C::NT * (R + 4); ldo = R + 4; }
+    O += (int64_t)(wc * (C::TN * 8) + 2 * t) * ldo + wr * (C::TM * 8) + gq;
+    const int colb = wc * (C::TN * 8) + 2 * t;
 #pragma unroll
     for (int j = 0; j < C::TN; ++j) {
-      const int col = wc * (C::TN * 8) + j * 8 + 2 * t;
 #pragma unroll
-      for (int i = 0; i < C::TM; ++i) {
-        const int row = wr * (C::TM * 8) + i * 8 + gq;
+      for (int e = 0; e < 2; ++e) {
+        const bool live = colb + j * 8 + e < ncols && !dbg_nostore;
+        double* dcol = O + (int64_t)(j * 8 + e) * ldo;
 #pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          if (col + e < ncols) {
-            double* dst = O + (int64_t)(col + e) * ldo + row;
+        for (int i = 0; i < C::TM; ++i) {
+          if (live) {
             double v = acc[i][j][e];
             if (DOWN) {
               v *= p.alpha;
-              if (p.beta != 0.0) v += p.beta * (*dst);  // beta == 0 never reads Y (matmul.jl:13)
+              if (p.beta != 0.0) v += p.beta * dcol[i * 8];  // beta == 0 never reads Y (matmul.jl:13)
             }
-            *dst = v;
+            dcol[i * 8] = v;
           }
           acc[i][j][e] = 0.0;
         }

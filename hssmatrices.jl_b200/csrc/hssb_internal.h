@@ -61,6 +61,7 @@ struct CallParams {
   int64_t ldx, ldy;
   int32_t nrhs;
   double alpha, beta;
+  int32_t debug;  // HSSB_OPT_DEBUG bits: 1 = leaf kernels compute without waiting for data, 2 = move data without computing
 };
 
 // ------------------------------------------------------------- host tree ---
@@ -133,6 +134,7 @@ struct hssb_matrix {
   void* nccl_comm = nullptr;
   // options
   bool force_generic = false, use_graph = false, fused_leaf = false, profile = false;
+  int debug_mode = 0;
   std::vector<cudaEvent_t> prof_events;  // HSSB_OPT_PROFILE: one event between consecutive phases
   int64_t prof_nrhs = 0;
   // synthetic

@@ -155,6 +155,8 @@ int hssb_sync(hssb_matrix* h);
 #define HSSB_OPT_USE_GRAPH 2     /* 1: replay the level schedule as a CUDA graph              */
 #define HSSB_OPT_FUSED_LEAF 3    /* 1: form D*X in the upsweep leaf kernel (north-star variant) */
 #define HSSB_OPT_PROFILE 4       /* 1: record a CUDA event between phases (hssb_phase_time)   */
+#define HSSB_OPT_DEBUG 5         /* measurement only, WRONG RESULTS: bit 0 = leaf kernels compute on whatever is in
+                                    shared memory without waiting for data, bit 1 = move data without computing */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
