@@ -18,6 +18,7 @@
 //   translate_kernel<R>            F1 = B12 Z2 + R1 F ; F2 = B21 Z1 + R2 F   one CTA per (parent, tile)
 #pragma once
 
+#include <cuda.h>
 #include <type_traits>
 
 #include "hssb_internal.h"
@@ -86,6 +87,16 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
                : "memory");
 }
 
+// 2-D tiled TMA load (UTMALDG) of a {16 rows x NT columns} box of the user's X through a tensor
+// map with 128-byte swizzle: the box lands as NT rows of 128 bytes whose 16-byte chunks are XORed
+// with (row & 7), which makes the B-fragment reads conflict free without padding.
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];\n" ::"r"(
+                   smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ------------------------------------------------------------- leaf shapes ---
 // Both leaf kernels are one template: a persistent, warp-specialised, streamed-A GEMM
 //     OUT[MO x NT] = [A0 | A1] * [X ; F]           (K = K0 + K1)
@@ -96,20 +107,26 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
 // Warp 8 is the producer: it issues one cp.async.bulk per column (so the shared-memory image can
 // carry the conflict-free +4 padding) and tracks completion in bytes on mbarriers.  Warps 0-7
 // only wait, load fragments and issue DMMAs; they hand buffers back through "empty" mbarriers.
+#ifndef HSSB_DOWN_WARPS
+#define HSSB_DOWN_WARPS 8
+#endif
 template <int M, int R, bool DOWN>
 struct StreamCfg {
   static constexpr int MO = DOWN ? M : R;
   static constexpr int K0 = M, K1 = DOWN ? R : 0;
   static constexpr int NT = DOWN ? 8192 / M : (M >= 256 ? 32 : 64);  // same tile as leaf-down so both share X tiles
+  static constexpr int NWARPS = DOWN ? HSSB_DOWN_WARPS : 8;           // consumer warps (one extra warp produces)
   static constexpr int WR = DOWN ? M / 32 : ((R >= 32 ? 2 : 1) > 64 / NT ? (R >= 32 ? 2 : 1) : 64 / NT);  // warps along OUT rows
-  static constexpr int WC = 8 / WR;                                  // warps along right-hand sides
+  static constexpr int WC = NWARPS / WR;                             // warps along right-hand sides
   static constexpr int TM = MO / WR / 8, TN = NT / WC / 8;           // DMMA tiles per warp
   static constexpr int KC = DOWN ? (M >= 256 ? 8 : 16) : (4096 / R > M ? M : 4096 / R);
   static constexpr int KSTEPS = KC / 4;
   static constexpr int NCH0 = K0 / KC, NCH1 = K1 / KC, NCH = NCH0 + NCH1;
-  static constexpr int LDX = K0 + 4, LDF = K1 + 4, LDA = MO + 4;
+  static constexpr int LDF = K1 + 4, LDA = MO + 4;
+  static constexpr int XSLABS = K0 / 16;                 // X block = XSLABS boxes of {16 rows x NT cols}, 128B-swizzled
+  static constexpr int XBUF = K0 * NT;                   // doubles per X buffer (dense)
   static constexpr int BAR_BYTES = 128;
-  static constexpr int FIXED_BYTES = BAR_BYTES + 8 * (2 * NT * LDX + (K1 ? NT * LDF : 0));
+  static constexpr int FIXED_BYTES = BAR_BYTES + 8 * (2 * XBUF + (K1 ? NT * LDF : 0));
   static constexpr int STAGE_BYTES = 8 * KC * LDA;
   static constexpr int FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
   static constexpr int NSTAGE = DOWN ? (FIT > 6 ? 6 : FIT) : 2;       // as deep a ring as shared memory allows
@@ -117,28 +134,29 @@ struct StreamCfg {
   // consumer has left item i-1 (the producer can be at most NSTAGE chunks ahead), so the
   // waits on f_empty / x_empty never hold up the A ring.
   static constexpr int CX = (NSTAGE < NCH0 - 1) ? NSTAGE : NCH0 - 1;
-  static constexpr int XPIECES = (NCH - CX) < 8 ? (NCH - CX) : 8;     // X(i+1) is spread over this many chunks
-  static constexpr int XPC = (NT + XPIECES - 1) / XPIECES;            // columns per slice
+  static constexpr int XPIECES = (NCH - CX) < XSLABS ? (NCH - CX) : XSLABS;  // X(i+1) is spread over this many chunks
   static constexpr size_t SMEM = FIXED_BYTES + (size_t)NSTAGE * STAGE_BYTES;
   static_assert(MO % (8 * WR) == 0 && NT % (8 * WC) == 0 && TM >= 1 && TN >= 1, "warp tiling");
-  static_assert(K0 % KC == 0 && K1 % KC == 0 && KC % 4 == 0 && NCH0 >= 1 && NSTAGE >= 2 && XPIECES >= 1, "chunking");
+  static_assert(K0 % KC == 0 && K1 % KC == 0 && KC % 4 == 0 && NCH0 >= 1 && NSTAGE >= 2 && XPIECES >= 1 && K0 % 16 == 0, "chunking");
+  static_assert(KSTEPS == 2 || KSTEPS % 4 == 0, "k-steps per chunk must be 2 or a multiple of 4 (swizzle bookkeeping)");
   static_assert(SMEM <= 232448 && 2 * NSTAGE + 6 <= BAR_BYTES / 8, "shared memory budget");
 };
 
 template <int M, int R, bool DOWN>
-__global__ void __launch_bounds__(288, 1)
-stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p) {
+__global__ void __launch_bounds__(StreamCfg<M, R, DOWN>::NWARPS * 32 + 32, 1)
+stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p, const __grid_constant__ CUtensorMap xmap) {
   using C = StreamCfg<M, R, DOWN>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  // X buffers first: the 128-byte swizzle needs 1024-byte aligned boxes
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + C::SMEM - C::BAR_BYTES);
   uint64_t* a_full = bars;                    // [NSTAGE]
   uint64_t* a_empty = bars + C::NSTAGE;       // [NSTAGE]
   uint64_t* x_full = bars + 2 * C::NSTAGE;    // [2]
   uint64_t* x_empty = x_full + 2;             // [2]
   uint64_t* f_full = x_empty + 2;             // [1]
   uint64_t* f_empty = f_full + 1;             // [1]
-  double* Xs = reinterpret_cast<double*>(smem_raw + C::BAR_BYTES);  // [2][NT][LDX]
-  double* Fs = Xs + 2 * C::NT * C::LDX;                             // [NT][LDF]
+  double* Xs = reinterpret_cast<double*>(smem_raw);                 // [2][XSLABS][NT][16], swizzled
+  double* Fs = Xs + 2 * C::XBUF;                                    // [NT][LDF]
   double* As = Fs + (C::K1 ? C::NT * C::LDF : 0);                   // [NSTAGE][KC][LDA]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,10 +167,10 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
   const int nrhs = p.nrhs;
 
   if (tid == 0) {
-    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 8); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], 8); }
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], C::NWARPS); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], C::NWARPS); }
     mbar_init(f_full, 1);
-    mbar_init(f_empty, 8);
+    mbar_init(f_empty, C::NWARPS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
   }
   __syncthreads();
@@ -161,24 +179,24 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
   auto item_cols = [&](int item) { return min(C::NT, nrhs - ((first + item) % ntiles) * C::NT); };
 
   const bool dbg_nowait = p.debug & 1, dbg_nomma = p.debug & 2, dbg_nostore = p.debug & 4;
-  if (warp == 8) {
+  if (warp == C::NWARPS) {
     if (dbg_nowait) return;
     // ====================== producer warp ======================
-    // X columns keep the user's layout (one 8*K0-byte bulk copy per column, so the shared image
-    // can carry the +4 padding); slice `piece` of `npieces` is issued per call.
+    // X keeps the user's layout in global memory: XSLABS tiled TMA loads per block, slice `piece`
+    // of `npieces` per call.  Columns beyond nrhs are zero filled by the TMA unit and still
+    // counted, so the expected byte count is always the full block.
     auto load_x = [&](int item, int piece, int npieces) {
       const GTask& tk = tasks[(first + item) / ntiles];
-      const int tile = (first + item) % ntiles, nc = item_cols(item), buf = item & 1;
+      const int tile = (first + item) % ntiles, buf = item & 1;
       if (piece == 0) {
         mbar_wait(&x_empty[buf], ((item >> 1) & 1) ^ 1);
-        if (lane == 0) mbar_expect_tx(&x_full[buf], (uint32_t)(nc * C::K0 * 8));
+        if (lane == 0) mbar_expect_tx(&x_full[buf], (uint32_t)(C::XBUF * 8));
         __syncwarp();
       }
-      const int per = (C::NT + npieces - 1) / npieces;
-      const int c0 = piece * per, c1 = min(nc, c0 + per);
-      const double* src = p.X + tk.b0 + (int64_t)tile * C::NT * p.ldx;
-      double* dst = Xs + buf * C::NT * C::LDX;
-      for (int c = c0 + lane; c < c1; c += 32) bulk_g2s(dst + c * C::LDX, src + (int64_t)c * p.ldx, C::K0 * 8, &x_full[buf]);
+      const int per = (C::XSLABS + npieces - 1) / npieces;
+      const int s0 = piece * per, s1 = min(C::XSLABS, s0 + per);
+      for (int sl = s0 + lane; sl < s1; sl += 32)
+        tma_load_2d(Xs + buf * C::XBUF + sl * (C::NT * 16), &xmap, (int)tk.b0 + sl * 16, tile * C::NT, &x_full[buf]);
     };
     auto load_f = [&](int item) {
       if (C::K1 == 0) return;
@@ -239,17 +257,27 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
     if (w.b0) mbar_wait(w.b0, w.p0);
     if (w.b1) mbar_wait(w.b1, w.p1);
   };
-  // One chunk: A fragments "N" from the ring stage, B fragments from X or F (ldb compile time).
-  auto chunk = [&](const double* A, const double* B, auto ldb_tag, const NextWait& nw) -> bool {
-    constexpr int LDB = decltype(ldb_tag)::value;
+  // One chunk.  A fragments: "N" operand from the ring stage.  B fragments: from the swizzled X
+  // block (XPART: element (k, j) at slab k/16, row j, 16-byte chunk ((k%16)/2) ^ (j%8)) or from
+  // the padded F block.  `kstep0` = index of the chunk's first k-step within the item.
+  auto chunk = [&](const double* A, const double* B, auto xpart_tag, int kstep0, const NextWait& nw) -> bool {
+    constexpr bool XPART = decltype(xpart_tag)::value;
     bool ok = true;
+    int sw[4];
+    if (XPART) {
+      const int qb = kstep0 & 3;  // non-zero only when a chunk is shorter than a 16-row slab (KSTEPS == 2)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) sw[q] = ((((qb + q) & 3) * 2 + (t >> 1)) ^ gq) * 2 + (t & 1);
+      B += (kstep0 >> 2) * (C::NT * 16);
+    }
 #pragma unroll
     for (int kk = 0; kk < C::KSTEPS; ++kk) {
       double a[C::TM], b[C::TN];
 #pragma unroll
       for (int i = 0; i < C::TM; ++i) a[i] = A[kk * 4 * C::LDA + i * 8];
 #pragma unroll
-      for (int j = 0; j < C::TN; ++j) b[j] = B[j * 8 * LDB + kk * 4];
+      for (int j = 0; j < C::TN; ++j)
+        b[j] = XPART ? B[(kk >> 2) * (C::NT * 16) + j * 8 * 16 + sw[kk & 3]] : B[j * 8 * C::LDF + kk * 4];
       if (kk == (C::KSTEPS >= 2 ? C::KSTEPS - 2 : 0)) ok = try_next(nw);
       if (!dbg_nomma) {
 #pragma unroll
@@ -274,7 +302,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
     // issue the loads the epilogue needs now; their latency hides behind the whole item
     const int task_i = (first + item) / ntiles, tile = (first + item) - task_i * ntiles;
     const int64_t out_row = tasks[task_i].c;
-    const double* Bx = Xs + buf * C::NT * C::LDX + (wc * (C::TN * 8) + gq) * C::LDX + t;
+    const double* Bx = Xs + buf * C::XBUF + (wc * (C::TN * 8) + gq) * 16;
 #pragma unroll 1
     for (int c = 0; c < C::NCH0; ++c) {
       const int nst = (st + 1 == C::NSTAGE) ? 0 : st + 1;
@@ -288,7 +316,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
           else { nw.b1 = &x_full[buf ^ 1]; nw.p1 = ((item + 1) >> 1) & 1; }
         }
       }
-      const bool ok = chunk(Abase + st * C::KC * C::LDA, Bx + c * C::KC, std::integral_constant<int, C::LDX>{}, nw);
+      const bool ok = chunk(Abase + st * C::KC * C::LDA, Bx, std::true_type{}, c * C::KSTEPS, nw);
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(&a_empty[st]);
@@ -309,7 +337,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
           nw.b0 = &a_full[nst]; nw.p0 = nph;
           if (last_f) { nw.b1 = &x_full[buf ^ 1]; nw.p1 = ((item + 1) >> 1) & 1; }
         }
-        const bool ok = chunk(Abase + st * C::KC * C::LDA, Bf + c * C::KC, std::integral_constant<int, (C::K1 ? C::LDF : 4)>{}, nw);
+        const bool ok = chunk(Abase + st * C::KC * C::LDA, Bf + c * C::KC, std::false_type{}, 0, nw);
         __syncwarp();
         if (lane == 0) {
           mbar_arrive(&a_empty[st]);
@@ -494,21 +522,48 @@ struct FastState {
   }
 };
 
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// Tensor map of the caller's X (rows x nrhs, column-major, leading dimension ldx): box {16, NT}, 128B swizzle.
+static int make_x_map(CUtensorMap* map, const double* X, int64_t rows, int64_t nrhs, int64_t ldx, int nt) {
+  static EncodeTiledFn encode = nullptr;
+  if (!encode) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    HSSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) HSSB_FAIL(HSSB_ERR_CUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    encode = (EncodeTiledFn)fn;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)rows, (cuuint64_t)nrhs};
+  const cuuint64_t gstr[1] = {(cuuint64_t)ldx * 8};
+  const cuuint32_t box[2] = {16, (cuuint32_t)nt};
+  const cuuint32_t estr[2] = {1, 1};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)X, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) HSSB_FAIL(HSSB_ERR_CUDA, "cuTensorMapEncodeTiled failed with code %d", (int)r);
+  return HSSB_OK;
+}
+
 template <int M, int R>
 static int launch_leaf(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st, bool down) {
   FastState* fs = (FastState*)H->fast_state;
+  CUtensorMap xmap;
   if (down) {
     using C = StreamCfg<M, R, true>;
     const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
     const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
+    if (int rc = make_x_map(&xmap, cp.X, H->local_n, cp.nrhs, cp.ldx, C::NT)) return rc;
     if (int rc = fs->configure((const void*)stream_leaf_kernel<M, R, true>, C::SMEM)) return rc;
-    stream_leaf_kernel<M, R, true><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
+    stream_leaf_kernel<M, R, true><<<grid, C::NWARPS * 32 + 32, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp, xmap);
   } else {
     using C = StreamCfg<M, R, false>;
     const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
     const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
+    if (int rc = make_x_map(&xmap, cp.X, H->local_n, cp.nrhs, cp.ldx, C::NT)) return rc;
     if (int rc = fs->configure((const void*)stream_leaf_kernel<M, R, false>, C::SMEM)) return rc;
-    stream_leaf_kernel<M, R, false><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
+    stream_leaf_kernel<M, R, false><<<grid, C::NWARPS * 32 + 32, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp, xmap);
   }
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
