@@ -189,7 +189,7 @@ def main():
         P.set_option(hb.OPT_FORCE_GENERIC, 1)
     if "fused" in variants:
         P.set_option(hb.OPT_FUSED_LEAF, 1)
-    P.set_option(hb.OPT_USE_GRAPH, 0 if ("nograph" in variants or N > 1) else 1)
+    P.set_option(hb.OPT_USE_GRAPH, 0 if "nograph" in variants else 1)
     rows = P.info.local_n
     # a dedicated non-default stream: the library launches on it and torch's events time it
     tstream = torch.cuda.Stream()
@@ -304,7 +304,7 @@ def main():
             "config": {"workload": cfg["desc"], "n_total": n_total, "leafsize": ls, "rank": r, "nrhs": k,
                        "parallelism": f"subtree-shard x{N}" if N > 1 else "single GPU", "variant": args.variant,
                        "l2": "working set (generators + X + Y = %.2f GB per GPU) >> 126 MB L2, no flush needed" % (bytes_local * 1e-9),
-                       "cuda_graph": bool(N == 1 and "nograph" not in variants)},
+                       "cuda_graph": bool("nograph" not in variants)},
             "hbm_gbs": gbs,
             "product_roofline": {
                 "flops": flops_all, "algorithmic_bytes": bytes_all, "t_mem_ms": t_mem * 1e3, "t_flop_ms": t_flop * 1e3,

@@ -109,7 +109,7 @@ SIGNATURES = {
     "hssb_debug_pool": (C.c_int, [_P, _P, _i64]),
 }
 
-OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_FUSED_LEAF, OPT_PROFILE, OPT_DEBUG = 1, 2, 3, 4, 5
+OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_FUSED_LEAF, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS = 1, 2, 3, 4, 5, 6
 PHASE_NAMES = ("leaf_up", "merge", "exchange", "translate", "leaf_down")
 KIND_NAMES = ("D", "U", "V", "B12", "B21", "R", "W")
 

@@ -720,7 +720,7 @@ static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
       H->launches += g.kernels;
       return HSSB_OK;
     }
-  if (H->graphs.size() >= 16) invalidate_graphs(H);
+  if (H->graphs.size() >= 64) invalidate_graphs(H);
   cudaGraph_t graph = nullptr;
   const int64_t before = H->launches;
   // capture on the library's own stream (the legacy default stream cannot be captured),
@@ -894,6 +894,11 @@ int hssb_destroy(hssb_matrix* h) {
   cudaFree(h->f_dev);
   cudaFree(h->x_stage);
   cudaFree(h->y_stage);
+  if (h->copy_in) {
+    cudaStreamDestroy(h->copy_in);
+    cudaStreamDestroy(h->copy_out);
+    for (int i = 0; i < hssb_matrix::MAX_BLOCKS; ++i) { cudaEventDestroy(h->ev_in[i]); cudaEventDestroy(h->ev_done[i]); }
+  }
   if (h->stream) cudaStreamDestroy(h->stream);
   cudaGetLastError();
   delete h;
@@ -981,7 +986,7 @@ int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs
   CallParams cp;
   cp.pool = h->pool_dev; cp.X = dX; cp.Y = dY; cp.Z = h->z_dev; cp.F = h->f_dev;
   cp.ldx = ldx; cp.ldy = ldy; cp.nrhs = (int32_t)nrhs; cp.alpha = alpha; cp.beta = beta; cp.debug = h->debug_mode;
-  if (h->use_graph && h->n_shards == 1) return run_graph(h, cp, st);
+  if (h->use_graph) return run_graph(h, cp, st);
   return run_phases(h, cp, st);
 }
 
@@ -1013,16 +1018,47 @@ int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, co
     invalidate_graphs(h);
   }
   const int64_t sx = std::max<int64_t>(h->local_n, 1), sy = h->local_m;
-  if (rows_x > 0)
-    HSSB_CUDA(cudaMemcpy2DAsync(h->x_stage, (size_t)sx * 8, X, (size_t)ldx * 8, (size_t)rows_x * 8, (size_t)nrhs,
-                                cudaMemcpyHostToDevice, h->stream));
-  if (beta != 0.0)
-    HSSB_CUDA(cudaMemcpy2DAsync(h->y_stage, (size_t)sy * 8, Y, (size_t)ldy * 8, (size_t)rows_y * 8, (size_t)nrhs,
-                                cudaMemcpyHostToDevice, h->stream));
-  int rc = hssb_matmul_dev(h, rows_y, rows_x, nrhs, h->x_stage, sx, h->y_stage, sy, alpha, beta, h->stream);
-  if (rc) return rc;
-  HSSB_CUDA(cudaMemcpy2DAsync(Y, (size_t)ldy * 8, h->y_stage, (size_t)sy * 8, (size_t)rows_y * 8, (size_t)nrhs,
-                              cudaMemcpyDeviceToHost, h->stream));
+  // The product is independent per right-hand side, so the call is pipelined over column blocks:
+  // H2D of block j+1 (copy-in stream), the product of block j (compute stream) and D2H of block
+  // j-1 (copy-out stream) overlap; PCIe is full duplex.  Blocks are a multiple of the widest
+  // kernel tile that still leaves >= 2 blocks, so the tiles stay full.
+  if (!h->copy_in) {
+    HSSB_CUDA(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+    HSSB_CUDA(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < hssb_matrix::MAX_BLOCKS; ++i) {
+      HSSB_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      HSSB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  int64_t cb = nrhs;
+  if (h->pipeline_cols > 0) cb = std::min<int64_t>(nrhs, h->pipeline_cols);
+  else if (nrhs >= 32 && (int64_t)(rows_x + rows_y) * nrhs * 8 >= ((int64_t)64 << 20)) cb = std::max<int64_t>(16, (nrhs + 3) / 4 / 16 * 16);
+  int64_t nblk = (nrhs + cb - 1) / cb;
+  if (nblk > hssb_matrix::MAX_BLOCKS) { cb = (nrhs + hssb_matrix::MAX_BLOCKS - 1) / hssb_matrix::MAX_BLOCKS; nblk = (nrhs + cb - 1) / cb; }
+  // copies of this call must not overtake the previous call's use of the staging buffers
+  HSSB_CUDA(cudaEventRecord(h->ev_done[0], h->stream));
+  HSSB_CUDA(cudaStreamWaitEvent(h->copy_in, h->ev_done[0], 0));
+  for (int64_t j = 0; j < nblk; ++j) {
+    const int64_t c0 = j * cb, nc = std::min(cb, nrhs - c0);
+    if (rows_x > 0)
+      HSSB_CUDA(cudaMemcpy2DAsync(h->x_stage + c0 * sx, (size_t)sx * 8, X + c0 * ldx, (size_t)ldx * 8, (size_t)rows_x * 8,
+                                  (size_t)nc, cudaMemcpyHostToDevice, h->copy_in));
+    if (beta != 0.0)
+      HSSB_CUDA(cudaMemcpy2DAsync(h->y_stage + c0 * sy, (size_t)sy * 8, Y + c0 * ldy, (size_t)ldy * 8, (size_t)rows_y * 8,
+                                  (size_t)nc, cudaMemcpyHostToDevice, h->copy_in));
+    HSSB_CUDA(cudaEventRecord(h->ev_in[j], h->copy_in));
+  }
+  for (int64_t j = 0; j < nblk; ++j) {
+    const int64_t c0 = j * cb, nc = std::min(cb, nrhs - c0);
+    HSSB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[j], 0));
+    int rc = hssb_matmul_dev(h, rows_y, rows_x, nc, h->x_stage + c0 * sx, sx, h->y_stage + c0 * sy, sy, alpha, beta, h->stream);
+    if (rc) { cudaStreamSynchronize(h->copy_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_out); return rc; }
+    HSSB_CUDA(cudaEventRecord(h->ev_done[j], h->stream));
+    HSSB_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_done[j], 0));
+    HSSB_CUDA(cudaMemcpy2DAsync(Y + c0 * ldy, (size_t)ldy * 8, h->y_stage + c0 * sy, (size_t)sy * 8, (size_t)rows_y * 8,
+                                (size_t)nc, cudaMemcpyDeviceToHost, h->copy_out));
+  }
+  HSSB_CUDA(cudaStreamSynchronize(h->copy_out));
   HSSB_CUDA(cudaStreamSynchronize(h->stream));
   return HSSB_OK;
 }
@@ -1043,6 +1079,7 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
     case HSSB_OPT_FUSED_LEAF: h->fused_leaf = value != 0; break;
     case HSSB_OPT_PROFILE: h->profile = value != 0; break;
     case HSSB_OPT_DEBUG: h->debug_mode = (int)value; break;
+    case HSSB_OPT_PIPELINE_COLS: h->pipeline_cols = value; break;
     default: HSSB_FAIL(HSSB_ERR_ARG, "hssb_set_option: unknown option %d", opt);
   }
   if (h->device < 0) return HSSB_OK;

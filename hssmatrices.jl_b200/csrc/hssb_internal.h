@@ -122,6 +122,11 @@ struct hssb_matrix {
   double* y_stage = nullptr;
   int64_t stage_nrhs = 0;
   cudaStream_t stream = nullptr;
+  // host entry: column-block pipeline (H2D | product | D2H)
+  static constexpr int MAX_BLOCKS = 16;
+  cudaStream_t copy_in = nullptr, copy_out = nullptr;
+  cudaEvent_t ev_in[MAX_BLOCKS] = {}, ev_done[MAX_BLOCKS] = {};
+  int64_t pipeline_cols = 0;  // 0 = automatic
   int64_t launches = 0;
   // global / local shape
   int64_t m = 0, n = 0, local_m = 0, local_n = 0, local_row0 = 0, local_col0 = 0;

@@ -157,6 +157,7 @@ int hssb_sync(hssb_matrix* h);
 #define HSSB_OPT_PROFILE 4       /* 1: record a CUDA event between phases (hssb_phase_time)   */
 #define HSSB_OPT_DEBUG 5         /* measurement only, WRONG RESULTS: bit 0 = leaf kernels compute on whatever is in
                                     shared memory without waiting for data, bit 1 = move data without computing */
+#define HSSB_OPT_PIPELINE_COLS 6 /* host entry: right-hand sides per pipelined block (0 = automatic)  */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
