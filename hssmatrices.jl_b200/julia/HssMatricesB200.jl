@@ -1,0 +1,135 @@
+# HssMatricesB200.jl — Julia binding of libhssb200.so (include/hssb200.h).
+#
+# Drop-in for ONE path of HssMatrices.jl v0.1.6: `hssA * X` / `mul!(C, hssA, X, α, β)` for
+# HssMatrix{Float64} and strided Float64 matrices (src/matmul.jl:13-62).  The Julia API is
+# unchanged: this file only adds MORE SPECIFIC methods of `*` and `mul!`; every other element
+# type / array type keeps falling through to the reference methods.
+#
+# NOTE: Julia is not installed in the image this library was built in, so this file has never
+# been executed there; the same C ABI is exercised by the Python ctypes harness
+# (hssmatrices.jl_b200/__init__.py) that the tests and benchmarks use.  See INTEGRATION.md.
+module HssMatricesB200
+
+using HssMatrices
+using HssMatrices: HssMatrix, isleaf, gensize
+using LinearAlgebra
+import Base: *
+import LinearAlgebra: mul!
+
+const libhssb = get(ENV, "HSSB200_LIB", joinpath(@__DIR__, "..", "lib", "libhssb200.so"))
+
+struct HssbError <: Exception
+  code::Cint
+  msg::String
+end
+
+function check(rc::Integer)
+  rc >= 0 && return rc
+  msg = unsafe_string(ccall((:hssb_last_error, libhssb), Cstring, ()))
+  rc == -2 && throw(DimensionMismatch(msg))   # same exception type as src/matmul.jl:19-20
+  throw(HssbError(Cint(rc), msg))
+end
+
+"""Device-resident packed copy of an HssMatrix (hssb_matrix*)."""
+mutable struct PackedHss
+  handle::Ptr{Cvoid}
+  m::Int
+  n::Int
+  function PackedHss(handle, m, n)
+    p = new(handle, m, n)
+    finalizer(p) do q
+      q.handle == C_NULL || ccall((:hssb_destroy, libhssb), Cint, (Ptr{Cvoid},), q.handle)
+      q.handle = C_NULL
+    end
+    return p
+  end
+end
+Base.size(p::PackedHss) = (p.m, p.n)
+Base.size(p::PackedHss, d::Integer) = size(p)[d]
+
+dptr(A::Matrix{Float64}) = isempty(A) ? Ptr{Float64}(C_NULL) : pointer(A)
+
+# Post-order walk of the pointer tree (src/hssmatrix.jl:11-34); the C++ packer copies every block
+# during the call, flattens the tree into level-ordered arrays and uploads them.
+function addnode(b::Ptr{Cvoid}, h::HssMatrix{Float64}, isroot::Bool)
+  if isleaf(h)
+    m, n = size(h.D)
+    kr, kw = isroot ? (0, 0) : (size(h.U, 2), size(h.V, 2))
+    GC.@preserve h begin
+      return check(ccall((:hssb_builder_add_leaf, libhssb), Int64,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+        b, m, n, kr, kw, dptr(h.D), max(m, 1), dptr(h.U), max(m, 1), dptr(h.V), max(n, 1)))
+    end
+  end
+  l = addnode(b, h.A11, false)
+  r = addnode(b, h.A22, false)
+  kr1, kw1 = gensize(h.A11); kr2, kw2 = gensize(h.A22)
+  if isroot   # rooted(): src/hssmatrix.jl:266, used at src/matmul.jl:24
+    GC.@preserve h begin
+      return check(ccall((:hssb_builder_add_branch, libhssb), Int64,
+        (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
+         Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+        b, l, r, 0, 0, dptr(h.B12), max(kr1, 1), dptr(h.B21), max(kr2, 1),
+        C_NULL, 1, C_NULL, 1, C_NULL, 1, C_NULL, 1))
+    end
+  end
+  kr, kw = gensize(h)
+  GC.@preserve h begin
+    return check(ccall((:hssb_builder_add_branch, libhssb), Int64,
+      (Ptr{Cvoid}, Int64, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64,
+       Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+      b, l, r, kr, kw, dptr(h.B12), max(kr1, 1), dptr(h.B21), max(kr2, 1),
+      dptr(h.R1), max(kr1, 1), dptr(h.W1), max(kw1, 1), dptr(h.R2), max(kr2, 1), dptr(h.W2), max(kw2, 1)))
+  end
+end
+
+"""
+    pack(hssA; device=0) -> PackedHss
+
+Flatten `hssA` (treated as root, like `rooted`) and upload it to GPU `device`.
+"""
+function pack(hssA::HssMatrix{Float64}; device::Integer=0)
+  bref = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:hssb_builder_create, libhssb), Cint, (Ref{Ptr{Cvoid}},), bref))
+  href = Ref{Ptr{Cvoid}}(C_NULL)
+  try
+    root = addnode(bref[], hssA, true)
+    check(ccall((:hssb_builder_finalize, libhssb), Cint, (Ptr{Cvoid}, Int64, Cint, Cint, Cint, Ref{Ptr{Cvoid}}),
+                bref[], root, device, 0, 1, href))
+  finally
+    ccall((:hssb_builder_destroy, libhssb), Cvoid, (Ptr{Cvoid},), bref[])
+  end
+  return PackedHss(href[], size(hssA, 1), size(hssA, 2))
+end
+
+# mul!(C, hssA, B, α, β): src/matmul.jl:18-28.  β == 0 never reads C (src/matmul.jl:13 passes
+# uninitialised memory).
+function mul!(C::StridedMatrix{Float64}, p::PackedHss, B::StridedMatrix{Float64}, α::Real, β::Real)
+  size(p, 2) == size(B, 1) || throw(DimensionMismatch("First dimension of B does not match second dimension of A. Expected $(size(p, 2)), got $(size(B, 1))"))
+  size(C) == (size(p, 1), size(B, 2)) || throw(DimensionMismatch("Dimensions of C don't match up with A and B."))
+  (stride(B, 1) == 1 && stride(C, 1) == 1) || throw(ArgumentError("B and C need unit stride in the first dimension"))
+  GC.@preserve B C begin
+    check(ccall((:hssb_matmul, libhssb), Cint,
+      (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Float64),
+      p.handle, size(C, 1), size(B, 1), size(B, 2), pointer(B), max(stride(B, 2), 1), pointer(C), max(stride(C, 2), 1),
+      Float64(α), Float64(β)))
+  end
+  return C
+end
+*(p::PackedHss, B::StridedMatrix{Float64}) = mul!(Matrix{Float64}(undef, size(p, 1), size(B, 2)), p, B, 1.0, 0.0)   # src/matmul.jl:13
+*(p::PackedHss, x::StridedVector{Float64}) = reshape(p * reshape(x, length(x), 1), length(x))                      # src/matmul.jl:15
+
+# ---- drop-in methods on HssMatrix{Float64} ---------------------------------------------------
+# HssMatrix is mutable (recompress!, prune_leaves!, field assignment as in test/runtests.jl:75), so
+# the device copy is cached per object identity and must be dropped by hand after a mutation.
+const CACHE = IdDict{HssMatrix{Float64}, PackedHss}()
+packed(hssA::HssMatrix{Float64}) = get!(() -> pack(hssA), CACHE, hssA)
+"""Forget the device copy of `hssA` (call after mutating it)."""
+invalidate!(hssA::HssMatrix{Float64}) = (delete!(CACHE, hssA); nothing)
+
+mul!(C::StridedMatrix{Float64}, hssA::HssMatrix{Float64}, B::StridedMatrix{Float64}, α::Real, β::Real) = mul!(C, packed(hssA), B, α, β)
+*(hssA::HssMatrix{Float64}, B::StridedMatrix{Float64}) = packed(hssA) * B
+
+export pack, PackedHss, invalidate!
+
+end # module
