@@ -105,6 +105,10 @@ struct BlockSource {  // per node: either host copies or nothing (synthetic)
   const HostBlock* blk[BK_COUNT] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
+// V and W are only ever applied transposed (matmul.jl:34, :39): the pool stores V' and W' so that
+// every generator is a plain column-major "N" operand for the kernels.
+static inline bool stored_transposed(int kind) { return kind == BK_V || kind == BK_W; }
+
 static void block_shape(const std::vector<Node>& nodes, const Node& t, int kind, int64_t& rows, int64_t& cols) {
   rows = cols = 0;
   const Node* par = t.parent >= 0 ? &nodes[(size_t)t.parent] : nullptr;
@@ -115,7 +119,7 @@ static void block_shape(const std::vector<Node>& nodes, const Node& t, int kind,
     case BK_B12: if (!t.leaf && !t.remote) { rows = nodes[(size_t)t.left].kr; cols = nodes[(size_t)t.right].kw; } break;
     case BK_B21: if (!t.leaf && !t.remote) { rows = nodes[(size_t)t.right].kr; cols = nodes[(size_t)t.left].kw; } break;
     case BK_R: if (par) { rows = t.kr; cols = par->kr; } break;
-    case BK_W: if (par) { rows = t.kw; cols = par->kw; } break;
+    case BK_W: if (par) { rows = par->kw; cols = t.kw; } break;  // stored TRANSPOSED (W' is kw(parent) x kw)
     default: break;
   }
 }
@@ -290,8 +294,8 @@ static void build_plan(hssb_matrix* H) {
     const Node& l = nodes[(size_t)t.left];
     const Node& r = nodes[(size_t)t.right];
     GTask g = blank();
-    g.a0 = l.off[BK_W]; g.lda0 = l.ld[BK_W]; g.ta0 = 1; g.sb0 = SRC_Z; g.b0 = l.zoff; g.ldb0 = l.ldz; g.K0 = (int32_t)l.kw;
-    g.a1 = r.off[BK_W]; g.lda1 = r.ld[BK_W]; g.ta1 = 1; g.sb1 = SRC_Z; g.b1 = r.zoff; g.ldb1 = r.ldz; g.K1 = (int32_t)r.kw;
+    g.a0 = l.off[BK_W]; g.lda0 = l.ld[BK_W]; g.ta0 = 0; g.sb0 = SRC_Z; g.b0 = l.zoff; g.ldb0 = l.ldz; g.K0 = (int32_t)l.kw;
+    g.a1 = r.off[BK_W]; g.lda1 = r.ld[BK_W]; g.ta1 = 0; g.sb1 = SRC_Z; g.b1 = r.zoff; g.ldb1 = r.ldz; g.K1 = (int32_t)r.kw;
     g.M = (int32_t)t.kw;
     g.sc = SRC_Z; g.c = t.zoff; g.ldc = t.ldz;
     return g;
@@ -448,7 +452,7 @@ static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src) {
     for (size_t i = 0; i < nodes.size(); ++i)
       for (int k = 0; k < BK_COUNT; ++k)
         if (nodes[i].off[k] >= 0)
-          pieces.push_back({nodes[i].off[k], (*src)[i].blk[k], nodes[i].ld[k], k == BK_V, nodes[i].rows[k], nodes[i].cols[k]});
+          pieces.push_back({nodes[i].off[k], (*src)[i].blk[k], nodes[i].ld[k], stored_transposed(k), nodes[i].rows[k], nodes[i].cols[k]});
     auto put = [](double* dst, const Piece& pc) {  // dst has leading dimension pc.ld
       if (!pc.tr) {
         for (int64_t j = 0; j < pc.cols; ++j) memcpy(dst + j * pc.ld, pc.hb->data.data() + j * pc.rows, (size_t)pc.rows * sizeof(double));
@@ -501,7 +505,7 @@ static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src) {
           b.off = t.off[k];
           b.key = synth_key(H->seed, t.heap_id, k);
           b.rows = (int32_t)t.rows[k]; b.cols = (int32_t)t.cols[k]; b.ld = t.ld[k];
-          b.transposed = (k == BK_V);
+          b.transposed = stored_transposed(k);
           b.c = IH4_SCALE * ((k == BK_R || k == BK_W) ? tscale : 1.0);
           sb.push_back(b);
         }
@@ -597,7 +601,7 @@ static void fill_pool_host(hssb_matrix* H, const std::vector<BlockSource>* src) 
     for (int k = 0; k < BK_COUNT; ++k) {
       if (t.off[k] < 0) continue;
       double* dst = H->pool_host.data() + t.off[k];
-      const bool tr = (k == BK_V);  // stored(i, j) = logical(j, i); logical block is cols x rows
+      const bool tr = stored_transposed(k);  // stored(i, j) = logical(j, i); logical block is cols x rows
       if (src) {
         const HostBlock* hb = (*src)[i].blk[k];
         for (int64_t j = 0; j < t.cols[k]; ++j)
@@ -947,7 +951,7 @@ int hssb_get_block(const hssb_matrix* h, int64_t node, int kind, double* out, in
     HSSB_CUDA(cudaMemcpy2D(tmp.data(), (size_t)rows * 8, h->pool_dev + t.off[kind], (size_t)t.ld[kind] * 8, (size_t)rows * 8,
                            (size_t)cols, cudaMemcpyDeviceToHost));
   }
-  if (kind == BK_V) {  // the pool holds V' (kw x n); hand back V (n x kw)
+  if (stored_transposed(kind)) {  // the pool holds V' / W'; hand back V (n x kw) / W (kw x kw(parent))
     for (int64_t j = 0; j < cols; ++j)
       for (int64_t i = 0; i < rows; ++i) out[i * cols + j] = tmp[(size_t)(j * rows + i)];
   } else {

@@ -14,8 +14,7 @@
 // Kernels
 //   stream_leaf_kernel<M,R,false>  Z = V' X               persistent, warp-specialised (TMA producer warp)
 //   stream_leaf_kernel<M,R,true>   Y = a (D X + U F) + b Y   same kernel, [D U] streamed by K chunks
-//   merge_kernel<R>                Z = W1' Z1 + W2' Z2                   one CTA per (node, column tile)
-//   translate_kernel<R>            F1 = B12 Z2 + R1 F ; F2 = B21 Z1 + R2 F   one CTA per (parent, tile)
+//   stream_node_kernel<R>          Z = W1' Z1 + W2' Z2  and  F1 = B12 Z2 + R1 F   persistent, warp-specialised
 #pragma once
 
 #include <cuda.h>
@@ -378,135 +377,150 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
   }
 }
 
-// =================================================================== merge ===
-// Z[R x NT] = W1'[R x R] Z1 + W2'[R x R] Z2 for one (node, column tile); 128 threads,
-// warp w owns columns w*NT/4 .. of the tile (R/8 x NT/32 DMMA tiles).
+// ============================================================ tree levels ===
+// Merges and translates share one persistent, warp-specialised kernel.  An item is one
+// (task, column tile):
+//     OUT[R x NT] = A0[R x R] * B0[R x NT] (+ A1[R x R] * B1[R x NT])
+//   merge      Z  = W1' Z1 + W2' Z2     (matmul.jl:39; the pool holds W')
+//   translate  F1 = B12 Z2 (+ R1 F)     (matmul.jl:52-56)
+// A0/A1 are padded pool blocks (one bulk copy each) streamed through a ring; B0/B1 are padded
+// workspace tiles (one bulk copy each), double buffered per item.  Consecutive tiles of one task
+// re-read A0/A1 from L2.  Same producer / consumer protocol as the leaf kernel.
 template <int R>
 struct NodeCfg {
-  static constexpr int NT = R >= 64 ? 32 : 64;
-  static constexpr int TN = NT / 32;  // column tiles per warp
+  static constexpr int NT = 64;
   static constexpr int LD = R + 4;
-  static constexpr size_t MERGE_SMEM = 128 + sizeof(double) * (2 * R * LD + 2 * NT * LD);
-  static constexpr size_t TRANS_SMEM = 128 + sizeof(double) * (2 * R * LD + 2 * NT * LD);
+  static constexpr int WR = R >= 32 ? 2 : 1, WC = 8 / WR;
+  static constexpr int TM = R / WR / 8, TN = NT / WC / 8;
+  static constexpr int KSTEPS = R / 4;
+  static constexpr int TILE = NT * LD;                 // doubles per B tile
+  static constexpr int STAGE = R * LD;                 // doubles per A block
+  static constexpr int BAR_BYTES = 128;
+  static constexpr int FIXED_BYTES = BAR_BYTES + 8 * (2 * 2 * TILE);
+  static constexpr int FIT = (R >= 64 ? 232448 : 113000) - FIXED_BYTES;   // R < 64: leave room for 2 CTAs per SM
+  static constexpr int NSTAGE = FIT / (8 * STAGE) > 4 ? 4 : FIT / (8 * STAGE);
+  static constexpr size_t SMEM = FIXED_BYTES + (size_t)NSTAGE * 8 * STAGE;
+  static constexpr int CTAS_PER_SM = R >= 64 ? 1 : 2;
+  static_assert(NSTAGE >= 2 && TM >= 1 && TN >= 1 && 2 * NSTAGE + 4 <= BAR_BYTES / 8, "node kernel configuration");
 };
 
-// acc += op(A) * B over K = R for a warp's R x (8*TN) slab.  A "T": A(i,k) at As[i*LD + k]; "N": As[k*LD + i].
-template <int R, bool TRANS_A>
-__device__ __forceinline__ void node_mma(double (&acc)[R / 8][NodeCfg<R>::TN][2], const double* As, const double* Bs, int g, int t) {
-  using C = NodeCfg<R>;
-#pragma unroll
-  for (int kk = 0; kk < R / 4; ++kk) {
-    double b[C::TN];
-#pragma unroll
-    for (int j = 0; j < C::TN; ++j) b[j] = Bs[(j * 8 + g) * C::LD + kk * 4 + t];
-#pragma unroll
-    for (int i = 0; i < R / 8; ++i) {
-      const double a = TRANS_A ? As[(i * 8 + g) * C::LD + kk * 4 + t] : As[(kk * 4 + t) * C::LD + i * 8 + g];
-#pragma unroll
-      for (int j = 0; j < C::TN; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a, b[j]);
-    }
-  }
-}
-
 template <int R>
-__device__ __forceinline__ void node_store(const double (&acc)[R / 8][NodeCfg<R>::TN][2], double* O, int col0, int ncols, int g, int t) {
-  using C = NodeCfg<R>;
-#pragma unroll
-  for (int j = 0; j < C::TN; ++j)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = col0 + j * 8 + 2 * t + e;
-      if (col < ncols) {
-#pragma unroll
-        for (int i = 0; i < R / 8; ++i) O[(int64_t)col * C::LD + i * 8 + g] = acc[i][j][e];
-      }
-    }
-}
-
-template <int R>
-__global__ void __launch_bounds__(128)
-merge_kernel(const GTask* __restrict__ tasks, CallParams p) {
+__global__ void __launch_bounds__(288, NodeCfg<R>::CTAS_PER_SM)
+stream_node_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p) {
   using C = NodeCfg<R>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  double* Ws = reinterpret_cast<double*>(smem_raw + 128);  // [2][R][LD]   W(k, i) at Ws[i*LD + k]  ("T" operand)
-  double* Zs = Ws + 2 * R * C::LD;                         // [2][NT][LD]
-  const GTask tk = tasks[blockIdx.x];
-  const int tile = blockIdx.y, nrhs = p.nrhs;
-  const int ncols = min(C::NT, nrhs - tile * C::NT);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const int64_t toff = (int64_t)tile * C::NT * C::LD;
+  double* Bt = reinterpret_cast<double*>(smem_raw);            // [2 buffers][2 operands][NT][LD]
+  double* As = Bt + 4 * C::TILE;                               // [NSTAGE][R][LD]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + C::SMEM - C::BAR_BYTES);
+  uint64_t* a_full = bars;
+  uint64_t* a_empty = bars + C::NSTAGE;
+  uint64_t* b_full = bars + 2 * C::NSTAGE;   // [2]
+  uint64_t* b_empty = b_full + 2;            // [2]
 
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nitems = ntasks * ntiles;
+  const int first = (int)(((int64_t)blockIdx.x * nitems) / gridDim.x);
+  const int last = (int)(((int64_t)(blockIdx.x + 1) * nitems) / gridDim.x);
+  const int my = last - first;
+  const int nrhs = p.nrhs;
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&b_full[s], 1); mbar_init(&b_empty[s], 8); }
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    constexpr uint32_t wb = R * C::LD * 8;
-    const uint32_t zb = (uint32_t)(ncols * C::LD * 8);
-    mbar_expect_tx(bar, 2 * wb + 2 * zb);
-    bulk_g2s(Ws, p.pool + tk.a0, wb, bar);
-    bulk_g2s(Ws + R * C::LD, p.pool + tk.a1, wb, bar);
-    bulk_g2s(Zs, p.Z + tk.b0 * (int64_t)nrhs + toff, zb, bar);
-    bulk_g2s(Zs + C::NT * C::LD, p.Z + tk.b1 * (int64_t)nrhs + toff, zb, bar);
-  }
-  __syncthreads();  // the barrier is initialised before anyone polls it
-  mbar_wait(bar, 0);
-
-  double acc[R / 8][C::TN][2];
-#pragma unroll
-  for (int i = 0; i < R / 8; ++i)
-#pragma unroll
-    for (int j = 0; j < C::TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  const int col0 = warp * (C::NT / 4);
-  node_mma<R, true>(acc, Ws, Zs + col0 * C::LD, g, t);
-  node_mma<R, true>(acc, Ws + R * C::LD, Zs + (C::NT + col0) * C::LD, g, t);
-  node_store<R>(acc, p.Z + tk.c * (int64_t)nrhs + toff, col0, ncols, g, t);
-}
-
-// =============================================================== translate ===
-// One task = one child: F_c[R x NT] = B[R x R] Z_sibling (+ R_c[R x R] F_parent); one CTA per
-// (task, column tile), 128 threads.
-template <int R>
-__global__ void __launch_bounds__(128)
-translate_kernel(const GTask* __restrict__ tasks, CallParams p) {
-  using C = NodeCfg<R>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
-  double* Bs = reinterpret_cast<double*>(smem_raw + 128);  // [R][LD]  B12 or B21   A(i,k) at [k*LD + i]  ("N" operand)
-  double* Rs = Bs + R * C::LD;         // [R][LD]  R of the child
-  double* Zs = Rs + R * C::LD;         // [NT][LD] Z of the sibling
-  double* Fs = Zs + C::NT * C::LD;     // [NT][LD] F of the parent
-  const GTask tk = tasks[blockIdx.x];
-  const int tile = blockIdx.y, nrhs = p.nrhs;
-  const int ncols = min(C::NT, nrhs - tile * C::NT);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
-  const bool has_f = tk.K1 > 0;
-  const int64_t toff = (int64_t)tile * C::NT * C::LD;
-
-  if (tid == 0) {
-    mbar_init(bar, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    constexpr uint32_t gb = R * C::LD * 8;
-    const uint32_t zb = (uint32_t)(ncols * C::LD * 8);
-    mbar_expect_tx(bar, has_f ? 2 * (gb + zb) : gb + zb);
-    bulk_g2s(Bs, p.pool + tk.a0, gb, bar);
-    bulk_g2s(Zs, p.Z + tk.b0 * (int64_t)nrhs + toff, zb, bar);
-    if (has_f) {
-      bulk_g2s(Rs, p.pool + tk.a1, gb, bar);
-      bulk_g2s(Fs, p.F + tk.b1 * (int64_t)nrhs + toff, zb, bar);
-    }
   }
   __syncthreads();
-  mbar_wait(bar, 0);
+  if (my <= 0) return;
+  const bool two = tasks[0].K1 > 0;  // uniform over the launch (false only for the root translate)
+  const int nch = two ? 2 : 1;
+  auto ws = [&](int src) -> const double* { return src == SRC_F ? p.F : p.Z; };
 
-  double acc[R / 8][C::TN][2];
+  if (warp == 8) {
+    // ====================== producer warp ======================
+    if (lane != 0) return;
+    auto load_b = [&](int item) {
+      const GTask& tk = tasks[(first + item) / ntiles];
+      const int tile = (first + item) % ntiles, buf = item & 1;
+      const uint32_t bytes = (uint32_t)(min(C::NT, nrhs - tile * C::NT) * C::LD * 8);
+      const int64_t toff = (int64_t)tile * C::TILE;
+      mbar_wait(&b_empty[buf], ((item >> 1) & 1) ^ 1);
+      mbar_expect_tx(&b_full[buf], two ? 2 * bytes : bytes);
+      bulk_g2s(Bt + (buf * 2) * C::TILE, ws(tk.sb0) + tk.b0 * (int64_t)nrhs + toff, bytes, &b_full[buf]);
+      if (two) bulk_g2s(Bt + (buf * 2 + 1) * C::TILE, ws(tk.sb1) + tk.b1 * (int64_t)nrhs + toff, bytes, &b_full[buf]);
+    };
+    load_b(0);
+    int g = 0;
+    for (int item = 0; item < my; ++item) {
+      const GTask& tk = tasks[(first + item) / ntiles];
+      for (int c = 0; c < nch; ++c, ++g) {
+        const int st = g % C::NSTAGE;
+        mbar_wait(&a_empty[st], ((g / C::NSTAGE) & 1) ^ 1);
+        mbar_expect_tx(&a_full[st], C::STAGE * 8);
+        bulk_g2s(As + st * C::STAGE, p.pool + (c ? tk.a1 : tk.a0), C::STAGE * 8, &a_full[st]);
+      }
+      // in order of need: this item's A blocks first, then the next item's B tiles (their buffer
+      // frees up when the consumers leave item-1)
+      if (item + 1 < my) load_b(item + 1);
+    }
+    return;
+  }
+
+  // ====================== consumer warps ======================
+  const int gq = lane >> 2, t = lane & 3;
+  const int wr = warp % C::WR, wc = warp / C::WR;
+  double acc[C::TM][C::TN][2];
 #pragma unroll
-  for (int i = 0; i < R / 8; ++i)
+  for (int i = 0; i < C::TM; ++i)
 #pragma unroll
     for (int j = 0; j < C::TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-  const int col0 = warp * (C::NT / 4);
-  node_mma<R, false>(acc, Bs, Zs + col0 * C::LD, g, t);
-  if (has_f) node_mma<R, false>(acc, Rs, Fs + col0 * C::LD, g, t);
-  node_store<R>(acc, p.F + tk.c * (int64_t)nrhs + toff, col0, ncols, g, t);
+  const double* Abase = As + wr * (C::TM * 8) + gq + t * C::LD;
+  const double* Bbase = Bt + (wc * (C::TN * 8) + gq) * C::LD + t;
+  int st = 0;
+  uint32_t ph = 0;
+  for (int item = 0; item < my; ++item) {
+    const int buf = item & 1;
+    const int task_i = (first + item) / ntiles, tile = (first + item) - task_i * ntiles;
+    const int64_t out_row = tasks[task_i].c;
+    const int out_src = tasks[task_i].sc;
+    mbar_wait(&b_full[buf], (item >> 1) & 1);
+    for (int c = 0; c < nch; ++c) {
+      mbar_wait(&a_full[st], ph);
+      const double* A = Abase + st * C::STAGE;
+      const double* B = Bbase + (buf * 2 + c) * C::TILE;
+#pragma unroll
+      for (int kk = 0; kk < C::KSTEPS; ++kk) {
+        double a[C::TM], b[C::TN];
+#pragma unroll
+        for (int i = 0; i < C::TM; ++i) a[i] = A[kk * 4 * C::LD + i * 8];
+#pragma unroll
+        for (int j = 0; j < C::TN; ++j) b[j] = B[j * 8 * C::LD + kk * 4];
+#pragma unroll
+        for (int i = 0; i < C::TM; ++i)
+#pragma unroll
+          for (int j = 0; j < C::TN; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&a_empty[st]);
+        if (c == nch - 1) mbar_arrive(&b_empty[buf]);
+      }
+      if (++st == C::NSTAGE) { st = 0; ph ^= 1; }
+    }
+    const int ncols = min(C::NT, nrhs - tile * C::NT);
+    double* O = (out_src == SRC_F ? p.F : p.Z) + out_row * (int64_t)nrhs + (int64_t)tile * C::TILE;
+    O += (int64_t)(wc * (C::TN * 8) + 2 * t) * C::LD + wr * (C::TM * 8) + gq;
+    const int colb = wc * (C::TN * 8) + 2 * t;
+#pragma unroll
+    for (int j = 0; j < C::TN; ++j)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const bool live = colb + j * 8 + e < ncols;
+#pragma unroll
+        for (int i = 0; i < C::TM; ++i) {
+          if (live) O[(int64_t)(j * 8 + e) * C::LD + i * 8] = acc[i][j][e];
+          acc[i][j][e] = 0.0;
+        }
+      }
+  }
 }
 
 // ================================================================ host side ===
@@ -575,13 +589,9 @@ static int launch_node(hssb_matrix* H, const Phase& ph, const CallParams& cp, cu
   using C = NodeCfg<R>;
   FastState* fs = (FastState*)H->fast_state;
   const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
-  if (ph.fast == FAST_MERGE) {
-    if (int rc = fs->configure((const void*)merge_kernel<R>, C::MERGE_SMEM)) return rc;
-    merge_kernel<R><<<dim3((unsigned)ph.ntasks, (unsigned)ntiles), 128, C::MERGE_SMEM, st>>>(H->tasks_dev + ph.task0, cp);
-  } else {
-    if (int rc = fs->configure((const void*)translate_kernel<R>, C::TRANS_SMEM)) return rc;
-    translate_kernel<R><<<dim3((unsigned)ph.ntasks, (unsigned)ntiles), 128, C::TRANS_SMEM, st>>>(H->tasks_dev + ph.task0, cp);
-  }
+  const int grid = (int)std::min<int64_t>(ph.ntasks * ntiles, (int64_t)fs->num_sms * C::CTAS_PER_SM);
+  if (int rc = fs->configure((const void*)stream_node_kernel<R>, C::SMEM)) return rc;
+  stream_node_kernel<R><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
   return HSSB_OK;
@@ -604,10 +614,10 @@ static void plan_fast_phases(hssb_matrix* H) {
       switch (ph.kind) {
         // the kernels rely on the padded (+4) leading dimensions of the pool and the workspaces
         case PH_LEAF_UP: ok = g.M == r && g.K0 == m && g.lda0 == r + 4 && g.ta0 == 0 && g.ldc == r + 4 && g.a0 >= 0; break;
-        case PH_MERGE: ok = g.M == r && g.K0 == r && g.K1 == r && g.lda0 == r + 4 && g.lda1 == r + 4 && g.ldb0 == r + 4 && g.ldb1 == r + 4 && g.ldc == r + 4 && g.a0 >= 0 && g.a1 >= 0; break;
+        case PH_MERGE: ok = g.M == r && g.K0 == r && g.K1 == r && g.lda0 == r + 4 && g.lda1 == r + 4 && g.ldb0 == r + 4 && g.ldb1 == r + 4 && g.ldc == r + 4 && g.a0 >= 0 && g.a1 >= 0 && !g.ta0 && !g.ta1; break;
         case PH_TRANSLATE:
           ok = g.M == r && g.K0 == r && (g.K1 == r || g.K1 == 0) && g.lda0 == r + 4 && g.ldb0 == r + 4 && g.ldc == r + 4 && g.a0 >= 0 &&
-               (g.K1 == 0 || (g.lda1 == r + 4 && g.ldb1 == r + 4 && g.a1 >= 0));
+               (g.K1 == 0 || (g.lda1 == r + 4 && g.ldb1 == r + 4 && g.a1 >= 0)) && g.K1 == tk[0].K1 && !g.ta0 && !g.ta1;
           break;
         case PH_LEAF_DOWN: ok = g.M == m && g.K0 == m && g.K1 == r && g.lda0 == m + 4 && g.lda1 == m + 4 && g.ldb1 == r + 4 && g.a0 >= 0 && g.a1 >= 0; break;
         default: ok = false;
