@@ -990,7 +990,9 @@ int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs
   CallParams cp;
   cp.pool = h->pool_dev; cp.X = dX; cp.Y = dY; cp.Z = h->z_dev; cp.F = h->f_dev;
   cp.ldx = ldx; cp.ldy = ldy; cp.nrhs = (int32_t)nrhs; cp.alpha = alpha; cp.beta = beta; cp.debug = h->debug_mode;
-  if (h->use_graph) return run_graph(h, cp, st);
+  // graph replay: always for the host entry (its staging pointers are stable), on request for
+  // caller-owned device pointers (a new pointer set costs a capture + instantiate)
+  if ((h->use_graph || h->in_host_call) && !h->profile) return run_graph(h, cp, st);
   return run_phases(h, cp, st);
 }
 
@@ -1055,7 +1057,9 @@ int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, co
   for (int64_t j = 0; j < nblk; ++j) {
     const int64_t c0 = j * cb, nc = std::min(cb, nrhs - c0);
     HSSB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[j], 0));
+    h->in_host_call = true;
     int rc = hssb_matmul_dev(h, rows_y, rows_x, nc, h->x_stage + c0 * sx, sx, h->y_stage + c0 * sy, sy, alpha, beta, h->stream);
+    h->in_host_call = false;
     if (rc) { cudaStreamSynchronize(h->copy_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_out); return rc; }
     HSSB_CUDA(cudaEventRecord(h->ev_done[j], h->stream));
     HSSB_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_done[j], 0));

@@ -75,7 +75,28 @@ __global__ void __launch_bounds__(256, 1) dmma_loop_kernel(double* out, int iter
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
   for (int it = 0; it < iters; ++it) {
-    if (VARIANT == 0) {
+    if (VARIANT == 2) {
+      // chunked like the kernel: 4 k-steps (64 DMMAs) per chunk, the chunk base changes at run time
+#pragma unroll 1
+      for (int c = 0; c < KC / 16; ++c) {
+        const double* A = As + (c * 16) * LDA + wm * 32 + g + t * LDA;
+        const double* B = Xs + (wn * 32 + g) * LDX + t + c * 16;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+          double a[4], b[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) a[i] = A[kk * 4 * LDA + i * 8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) b[j] = B[j * 8 * LDX + kk * 4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+        }
+        __syncwarp();
+        asm volatile("" ::: "memory");
+      }
+    } else if (VARIANT == 0) {
       const double* A = As + wm * 32 + g + t * LDA;
       const double* B = Xs + (wn * 32 + g) * LDX + t;
 #pragma unroll
@@ -184,7 +205,7 @@ extern "C" int hssb_measure_peak(int device, int kind, int64_t arg, double* out)
       if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
     }
     cudaFree(d);
-  } else if (kind == 4 || kind == 5) {
+  } else if (kind == 4 || kind == 5 || kind == 6) {
     // arg = CTAs per SM (1 or 2)
     const int per_sm = arg >= 1 && arg <= 2 ? (int)arg : 1;
     const int iters = 400, grid = prop.multiProcessorCount * per_sm;
@@ -193,10 +214,12 @@ extern "C" int hssb_measure_peak(int device, int kind, int64_t arg, double* out)
     HSSB_CUDA(cudaMalloc(&d, 64));
     HSSB_CUDA(cudaFuncSetAttribute(dmma_loop_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     HSSB_CUDA(cudaFuncSetAttribute(dmma_loop_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    HSSB_CUDA(cudaFuncSetAttribute(dmma_loop_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int rep = 0; rep < 4; ++rep) {
       HSSB_CUDA(cudaEventRecord(e0));
       if (kind == 4) dmma_loop_kernel<0><<<grid, 256, smem>>>(d, iters);
-      else dmma_loop_kernel<1><<<grid, 256, smem>>>(d, iters);
+      else if (kind == 5) dmma_loop_kernel<1><<<grid, 256, smem>>>(d, iters);
+      else dmma_loop_kernel<2><<<grid, 256, smem>>>(d, iters);
       HSSB_CUDA(cudaEventRecord(e1));
       HSSB_CUDA(cudaEventSynchronize(e1));
       float ms = 0;

@@ -140,6 +140,7 @@ struct hssb_matrix {
   // options
   bool force_generic = false, use_graph = false, fused_leaf = false, profile = false;
   int debug_mode = 0;
+  bool in_host_call = false;
   std::vector<cudaEvent_t> prof_events;  // HSSB_OPT_PROFILE: one event between consecutive phases
   int64_t prof_nrhs = 0;
   // synthetic

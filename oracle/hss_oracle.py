@@ -681,3 +681,148 @@ class LazySyntheticHss:
 
         down(1, 0, self.n, None)
         return out
+
+
+# --------------------------------------------------------------------------
+# Randomized HSS compression (fixture builder for BASELINE config 2: the
+# n = 2^16 Cauchy matrix cannot be compressed directly, the reference itself
+# would route a matrix-free operator through randcompress, hssmatrix.jl:86).
+# Restates src/compression.jl:278-294 (randcompress), :358-430 (_randcompress!)
+# and :433-444 (_interpolate).  Not on the hot path.
+# --------------------------------------------------------------------------
+class KernelOperator:
+    """Matrix-free A[i,j] = kernel(x_i, y_j) with a fixed diagonal; stands in for
+    the reference's LinearMap (src/linearmap.jl).  Products are evaluated block
+    by block (optionally on a torch device to make the fixture cheap)."""
+
+    def __init__(self, x, y, kernel, diag=None, block=4096, device=None):
+        self.x, self.y, self.kernel, self.diag, self.block, self.device = x, y, kernel, diag, block, device
+        self.shape = (len(x), len(y))
+
+    def getindex(self, I, J):
+        I, J = np.asarray(I, dtype=np.int64), np.asarray(J, dtype=np.int64)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            B = self.kernel(self.x[I][:, None], self.y[J][None, :])
+        if self.diag is not None:
+            B = np.where(I[:, None] == J[None, :], self.diag, B)
+        return B
+
+    def _apply(self, Om, transpose):
+        m, n = self.shape
+        rows, cols = (n, m) if transpose else (m, n)
+        out = np.empty((rows, Om.shape[1]))
+        if self.device is not None:
+            import torch
+            xs = torch.as_tensor(self.y if transpose else self.x, device=self.device)
+            ys = torch.as_tensor(self.x if transpose else self.y, device=self.device)
+            Omt = torch.as_tensor(Om, device=self.device)
+            for a in range(0, rows, self.block):
+                b = min(rows, a + self.block)
+                d = (xs[a:b, None] - ys[None, :]) if not transpose else (ys[None, :] - xs[a:b, None])
+                Bk = 1.0 / d
+                if self.diag is not None:
+                    ii = torch.arange(a, b, device=self.device)
+                    Bk[ii - a, ii] = self.diag
+                out[a:b] = (Bk @ Omt).cpu().numpy()
+            return out
+        for a in range(0, rows, self.block):
+            b = min(rows, a + self.block)
+            I = np.arange(a, b)
+            Bk = self.getindex(np.arange(cols), I).T if transpose else self.getindex(I, np.arange(cols))
+            out[a:b] = Bk @ Om
+        return out
+
+    def matmat(self, Om):
+        return self._apply(Om, False)
+
+    def rmatmat(self, Om):
+        return self._apply(Om, True)
+
+
+def _interpolate(A, atol, rtol):
+    """Interpolative decomposition, src/compression.jl:433-444: A[:, J] * X ~ A."""
+    if A.shape[1] == 0:
+        return np.zeros((0, 0)), np.zeros(0, dtype=np.int64)
+    _, Rm, p = _sla.qr(A, mode="economic", pivoting=True)
+    d = np.abs(np.diag(Rm))
+    tol = min(atol, rtol * d[0]) if d.size else 0.0
+    rk = int(np.sum(d > tol))
+    J = p[:rk]
+    Xp = _sla.solve_triangular(Rm[:rk, :rk], Rm[:rk, :], lower=False)
+    X = np.empty_like(Xp)
+    X[:, p] = Xp  # R[1:rk,1:rk] \ R[1:rk, invperm(p)]
+    return X, J
+
+
+def randcompress(Aop, rcl, ccl, kest, atol=1e-9, rtol=1e-9, noversampling=10, rng=None):
+    """src/compression.jl:278-294."""
+    rng = np.random.default_rng(0) if rng is None else rng
+    m, n = Aop.shape
+    Om_col = rng.standard_normal((n, kest + noversampling))
+    Om_row = rng.standard_normal((m, kest + noversampling))
+    Scol = Aop.matmat(Om_col)
+    Srow = Aop.rmatmat(Om_row)
+
+    def blkdiag(rc, cc, root):  # hss_blkdiag, :447-475
+        if rc.isleaf():
+            D = Aop.getindex(np.arange(*rc.data), np.arange(*cc.data))
+            return hss_leaf(D, rootnode=True) if root else hss_leaf(D, np.zeros((D.shape[0], 0)), np.zeros((D.shape[1], 0)))
+        z = np.zeros((0, 0))
+        A11, A22 = blkdiag(rc.left, cc.left, False), blkdiag(rc.right, cc.right, False)
+        return hss_branch(A11, A22, z, z, rootnode=True) if root else hss_branch(A11, A22, z, z, z, z, z, z, rootnode=False)
+
+    h = blkdiag(rcl, ccl, True)
+    return _randcompress(h, Aop, Scol, Srow, Om_col, Om_row, 0, 0, atol, rtol, True)[0]
+
+
+def _randcompress(h, Aop, Scol, Srow, Om_col, Om_row, ro, co, atol, rtol, rootnode):
+    """src/compression.jl:358-430."""
+    if h.leafnode:
+        Scol = Scol - h.D @ Om_col  # :360
+        Srow = Srow - h.D.T @ Om_row  # :361
+        Xcol, Jcol = _interpolate(Scol.T, atol, rtol)  # :366
+        h.U = Xcol.T.copy()
+        Scol = Scol[Jcol, :]
+        U = h.U
+        Jcol = ro + Jcol
+        Xrow, Jrow = _interpolate(Srow.T, atol, rtol)  # :373
+        h.V = Xrow.T.copy()
+        Srow = Srow[Jrow, :]
+        V = h.V
+        Jrow = co + Jrow
+        return h, Scol, Srow, Om_col, Om_row, Jcol, Jrow, U, V
+    (m1, n1), (m2, n2) = h.sz1, h.sz2
+    h.A11, Scol1, Srow1, Oc1, Or1, Jc1, Jr1, U1, V1 = _randcompress(
+        h.A11, Aop, Scol[:m1], Srow[:n1], Om_col[:n1], Om_row[:m1], ro, co, atol, rtol, False)
+    h.A22, Scol2, Srow2, Oc2, Or2, Jc2, Jr2, U2, V2 = _randcompress(
+        h.A22, Aop, Scol[m1:], Srow[n1:], Om_col[n1:], Om_row[m1:], ro + m1, co + n1, atol, rtol, False)
+    Oc2, Oc1 = V2.T @ Oc2, V1.T @ Oc1  # :385-386
+    Or2, Or1 = U2.T @ Or2, U1.T @ Or1  # :387-388
+    Jcol, Jrow = np.concatenate([Jc1, Jc2]), np.concatenate([Jr1, Jr2])
+    Om_col, Om_row = np.vstack([Oc1, Oc2]), np.vstack([Or1, Or2])
+    h.B12 = Aop.getindex(Jc1, Jr2)  # :395
+    h.B21 = Aop.getindex(Jc2, Jr1)  # :396
+    Scol = np.vstack([Scol1 - h.B12 @ Oc2, Scol2 - h.B21 @ Oc1])  # :398
+    Srow = np.vstack([Srow1 - h.B21.T @ Or2, Srow2 - h.B12.T @ Or1])  # :399
+    kr1, kw1 = gensize(h.A11)
+    kr2, kw2 = gensize(h.A22)
+    if rootnode:  # :401-412
+        h.R1, h.R2 = np.zeros((kr1, 0)), np.zeros((kr2, 0))
+        h.W1, h.W2 = np.zeros((kw1, 0)), np.zeros((kw2, 0))
+        h.rootnode = True
+        return h, Scol, Srow, Om_col, Om_row, Jcol, Jrow, np.zeros((kr1 + kr2, 0)), np.zeros((kw1 + kw2, 0))
+    Xcol, Jcl = _interpolate(Scol.T, atol, rtol)  # :415
+    h.R1, h.R2 = Xcol[:, :Scol1.shape[0]].T.copy(), Xcol[:, Scol1.shape[0]:].T.copy()
+    Scol, Jcol = Scol[Jcl, :], Jcol[Jcl]
+    U = np.vstack([h.R1, h.R2])
+    Xrow, Jrl = _interpolate(Srow.T, atol, rtol)  # :423
+    h.W1, h.W2 = Xrow[:, :Srow1.shape[0]].T.copy(), Xrow[:, Srow1.shape[0]:].T.copy()
+    Srow, Jrow = Srow[Jrl, :], Jrow[Jrl]
+    V = np.vstack([h.W1, h.W2])
+    return h, Scol, Srow, Om_col, Om_row, Jcol, Jrow, U, V
+
+
+def cauchy_operator(n, lo=-1.0, hi=1.0, diag=1.0, device=None):
+    """Matrix-free README kernel K(x,y) = 1/(x-y), diagonal `diag`, on n points."""
+    x = np.linspace(lo, hi, n)
+    return KernelOperator(x, x, lambda a, b: 1.0 / (a - b), diag=diag, device=device)

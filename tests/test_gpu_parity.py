@@ -90,6 +90,27 @@ def test_readme_cauchy_config1(gpu, oracle):
     assert relerr(Y, A @ X) <= 50e-6       # the reference's own assertion, runtests.jl:63-64
 
 
+def test_cauchy_config2(gpu, oracle):
+    """BASELINE config 2: Cauchy kernel n = 2^16, leafsize 64, atol = rtol = 1e-9, nrhs 64.  A dense
+    2^16 x 2^16 matrix (34 GB) cannot be compressed directly; like hss(::LinearMap) in the reference
+    (hssmatrix.jl:86) the fixture goes through the randomized compression, restated in the oracle
+    (its sampling products A*Omega run blockwise on the GPU through torch to keep the fixture cheap)."""
+    n, k = 2 ** 16, 64
+    op = oracle.cauchy_operator(n, device="cuda")
+    cl = oracle.bisection_cluster(n, 64)
+    h = oracle.randcompress(op, cl, cl, 30, 1e-9, 1e-9, rng=np.random.default_rng(16))
+    assert oracle.nleaves(h) == 1024 and oracle.checkdims(h)
+    X = np.random.default_rng(64).standard_normal((n, k))
+    ref = oracle.matmul(h, X)
+    tree = to_product_tree(gpu, h)
+    Y = tree @ X
+    assert relerr(Y, ref) <= TOL
+    assert relerr(Y, op.matmat(X)) <= 1e-6      # quality of the compressed fixture, not of the product
+    info = tree._packed.info
+    assert info.n_leaves == 1024 and info.uniform == 0   # variable ranks: the any-shape kernel
+    tree._packed.close()
+
+
 @pytest.mark.parametrize("n,ls,r,k", [(4096, 128, 32, 64), (8192, 128, 64, 128), (4096, 256, 64, 32), (2048, 128, 32, 7),
                                       (1000, 128, 32, 64), (4096, 64, 16, 20)])
 def test_synthetic_device_generated(gpu, oracle, n, ls, r, k):
@@ -143,6 +164,35 @@ def test_device_entry_and_synthetic_rhs(gpu, oracle):
         assert relerr(Yh[:, :n].T, ref) <= TOL
         assert np.isnan(Yh[:, n:]).all()      # padding rows untouched
         assert P.launch_count() > 0
+
+
+@pytest.mark.parametrize("k", [1, 9, 63, 65, 200])
+def test_uniform_tree_any_nrhs(gpu, oracle, k):
+    """Fixed-shape kernels with partial / multiple column tiles (nrhs not a multiple of anything)."""
+    n, ls, r, seed = 2048, 128, 32, 77
+    ref = oracle.matmul(oracle.synthetic_hss(n, ls, r, seed), oracle.synth_x(seed, n, k))
+    with gpu.synthetic(n, ls, r, seed) as P:
+        assert all(p["fast"] for p in P.phase_times())
+        assert relerr(P @ oracle.synth_x(seed, n, k), ref) <= TOL
+
+
+def test_unaligned_x_falls_back_to_generic(gpu, oracle):
+    """X with an odd leading dimension or an 8-byte-only aligned base cannot be read by TMA /
+    16-byte copies: the leaf phases must take the any-shape kernel and still be exact."""
+    import torch
+    n, ls, r, k, seed = 2048, 128, 32, 16, 5
+    ref = oracle.matmul(oracle.synthetic_hss(n, ls, r, seed), oracle.synth_x(seed, n, k))
+    Xh = torch.from_numpy(np.ascontiguousarray(oracle.synth_x(seed, n, k).T))
+    with gpu.synthetic(n, ls, r, seed) as P:
+        for ldx, shift in ((n + 1, 0), (n + 2, 1)):
+            buf = torch.zeros(k * ldx + 8, dtype=torch.float64, device="cuda")
+            X = buf[shift:shift + k * ldx].view(k, ldx)
+            X[:, :n] = Xh.cuda()
+            Y = torch.full((k, n), float("nan"), dtype=torch.float64, device="cuda")
+            torch.cuda.synchronize()
+            P.matmul_dev(X.data_ptr(), ldx, Y.data_ptr(), n, k, stream=torch.cuda.current_stream().cuda_stream)
+            torch.cuda.synchronize()
+            assert relerr(Y.cpu().numpy().T, ref) <= TOL
 
 
 def test_full_size_config3_properties(gpu, oracle):
