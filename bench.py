@@ -180,11 +180,36 @@ def main():
     n_total = cfg["n"] * N if cfg["scaling"] == "weak" else cfg["n"]
 
     P = hb.synthetic(n_total, ls, r, SEED, device=local, shard_rank=rank, n_shards=N)
-    if N > 1:
+    variants = set(args.variant.split(","))
+    exchange = None
+    if N > 1 and "nccl" not in variants:   # default: NVLink peer stores into IPC-mapped workspaces
+        ok = 1
+        try:
+            P.reserve(cfg["nrhs"])
+            blob = P.xchg_export()
+        except hb.HssbError:
+            ok, blob = 0, b""
+        blobs = [None] * N
+        dist.all_gather_object(blobs, blob)
+        if ok and all(len(b) == 128 for b in blobs):
+            try:
+                P.xchg_import(blobs)
+            except hb.HssbError:
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], device="cuda")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if flag.item() == 1:
+            exchange = "nvlink peer stores (CUDA IPC)"
+        else:                              # no peer access on this box: rebuild and use NCCL
+            P.close()
+            P = hb.synthetic(n_total, ls, r, SEED, device=local, shard_rank=rank, n_shards=N)
+    if N > 1 and exchange is None:         # exchange = one ncclAllGather per product
         uid = [hb.PackedHss.comm_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0)
         P.comm_init(uid[0], rank, N)
-    variants = set(args.variant.split(","))
+        exchange = "nccl all-gather"
     if "generic" in variants:
         P.set_option(hb.OPT_FORCE_GENERIC, 1)
     if "fused" in variants:
@@ -303,6 +328,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["desc"], "n_total": n_total, "leafsize": ls, "rank": r, "nrhs": k,
                        "parallelism": f"subtree-shard x{N}" if N > 1 else "single GPU", "variant": args.variant,
+                       "exchange": exchange,
                        "l2": "working set (generators + X + Y = %.2f GB per GPU) >> 126 MB L2, no flush needed" % (bytes_local * 1e-9),
                        "cuda_graph": bool("nograph" not in variants)},
             "hbm_gbs": gbs,

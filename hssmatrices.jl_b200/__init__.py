@@ -100,6 +100,8 @@ SIGNATURES = {
     "hssb_phase_time": (C.c_int, [_P, C.c_int, C.POINTER(_PhaseTime)]),
     "hssb_comm_unique_id": (C.c_int, [_P]),
     "hssb_comm_init": (C.c_int, [_P, _P, C.c_int, C.c_int]),
+    "hssb_xchg_export": (C.c_int, [_P, _P]),
+    "hssb_xchg_import": (C.c_int, [_P, _P, C.c_int]),
     "hssb_measure_peak": (C.c_int, [C.c_int, C.c_int, _i64, C.POINTER(C.c_double)]),
     "hssb_plan_only": (C.c_int, [_P, _i64, C.c_int, C.c_int, C.POINTER(_P)]),
     "hssb_plan_only_synthetic": (C.c_int, [_i64, _i64, _i64, C.c_uint64, C.c_int, C.c_int, C.POINTER(_P)]),
@@ -110,7 +112,7 @@ SIGNATURES = {
 }
 
 OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_FUSED_LEAF, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS = 1, 2, 3, 4, 5, 6
-PHASE_NAMES = ("leaf_up", "merge", "exchange", "translate", "leaf_down")
+PHASE_NAMES = ("leaf_up", "merge", "exchange", "translate", "leaf_down", "exchange_ack")
 KIND_NAMES = ("D", "U", "V", "B12", "B21", "R", "W")
 
 
@@ -541,6 +543,18 @@ class PackedHss:
     def comm_init(self, unique_id, rank, n_ranks):
         buf = (C.c_char * 128).from_buffer_copy(unique_id)
         _check(lib().hssb_comm_init(self._h, buf, rank, n_ranks))
+
+    def xchg_export(self):
+        """128-byte blob (two CUDA IPC handles) of this rank's exchange buffers; reserve() first."""
+        buf = (C.c_char * 128)()
+        _check(lib().hssb_xchg_export(self._h, buf))
+        return bytes(buf)
+
+    def xchg_import(self, blobs):
+        """`blobs`: the xchg_export() results of all ranks, in rank order."""
+        raw = b"".join(blobs)
+        buf = (C.c_char * len(raw)).from_buffer_copy(raw)
+        _check(lib().hssb_xchg_import(self._h, buf, len(blobs)))
 
     # plan export (tests) -------------------------------------------------------
     def debug_plan(self):

@@ -345,6 +345,7 @@ static void build_plan(hssb_matrix* H) {
       if (t.top && t.depth == d) translate_tasks(t, true);
     add_phase(H, PH_TRANSLATE, d, true, batch);
   }
+  if (P > 1) { Phase ph; ph.kind = PH_XCHG_ACK; H->phases.push_back(ph); }  // gathered Z blocks are consumed from here on
   for (int d = p; d <= (int)H->depth; ++d) {
     for (auto& t : nodes)
       if (t.local && !t.leaf && t.depth == d) translate_tasks(t, false);
@@ -526,6 +527,9 @@ static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src) {
 
 static int ensure_workspace(hssb_matrix* H, int64_t nrhs) {
   if (nrhs <= H->ws_nrhs) return HSSB_OK;
+  if (H->xchg_exported)
+    HSSB_FAIL(HSSB_ERR_STATE, "the Z workspace is mapped by peer ranks: hssb_reserve(max_nrhs) before hssb_xchg_export (have %lld, need %lld)",
+              (long long)H->ws_nrhs, (long long)nrhs);
   if (H->z_dev) cudaFree(H->z_dev);
   if (H->f_dev) cudaFree(H->f_dev);
   H->z_dev = H->f_dev = nullptr;
@@ -658,6 +662,84 @@ static int load_nccl() {
                 g_nccl.GetErrorString ? g_nccl.GetErrorString(_r) : "?", __FILE__, __LINE__);             \
   } while (0)
 
+// --------------------------------------------------- peer-memory exchange ---
+// One-shot all-gather of the subtree-root Z blocks over NVLink peer stores, replacing the NCCL
+// call on the critical path: every rank writes its slot straight into the Z workspace of every
+// peer, then raises a flag there; the consumer spins on its own flag block.  An acknowledgement
+// flag (written after the last top-tree phase) keeps a fast rank from overwriting a slot a slow
+// peer is still reading.  Epochs live in device memory so that the kernels replay inside a graph.
+struct XchgParams {
+  double* z[hssb_matrix::MAX_PEERS];
+  unsigned long long* flags[hssb_matrix::MAX_PEERS];
+  int rank, nranks;
+  long long slot_off;    // element offset of slot 0 in every Z workspace
+  long long slot_elems;  // elements per slot
+};
+
+__device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void spin_until_ge(const unsigned long long* p, unsigned long long want) {
+  const long long t0 = clock64();
+  while (ld_volatile_sys(p) < want) {
+    if (clock64() - t0 > 8000000000ll) __trap();  // a lost peer must surface as an error, not a hang
+  }
+}
+
+__global__ void __launch_bounds__(256) xchg_push_kernel(XchgParams q) {
+  const int P = q.nranks, me = q.rank;
+  unsigned long long* mine = q.flags[me];
+  __shared__ unsigned long long s_epoch;
+  if (threadIdx.x == 0) s_epoch = ld_volatile_sys(mine + 2 * P) + 1;
+  __syncthreads();
+  const unsigned long long e = s_epoch;
+  // peers must have consumed the previous epoch before their copy of my slot is overwritten
+  if ((int)threadIdx.x < P && (int)threadIdx.x != me) spin_until_ge(mine + P + threadIdx.x, e - 1);
+  __syncthreads();
+  const double2* src = reinterpret_cast<const double2*>(q.z[me] + q.slot_off + (long long)me * q.slot_elems);
+  const long long n2 = q.slot_elems / 2;
+  for (int r = 0; r < P; ++r) {
+    if (r == me) continue;
+    double2* dst = reinterpret_cast<double2*>(q.z[r] + q.slot_off + (long long)me * q.slot_elems);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n2; i += (long long)gridDim.x * blockDim.x) dst[i] = src[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  __shared__ bool s_last;
+  if (threadIdx.x == 0) s_last = atomicAdd(mine + 2 * P + 1, 1ull) == gridDim.x - 1;
+  __syncthreads();
+  if (s_last) {  // every CTA of this rank has pushed: publish, then wait for everybody else's slot
+    if (threadIdx.x == 0) mine[2 * P + 1] = 0;
+    if ((int)threadIdx.x < P && (int)threadIdx.x != me) {
+      __threadfence_system();
+      asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(q.flags[threadIdx.x] + me), "l"(e) : "memory");
+      spin_until_ge(mine + threadIdx.x, e);
+    }
+    __syncthreads();
+    __threadfence_system();
+    if (threadIdx.x == 0) mine[2 * P] = e;
+  }
+}
+
+__global__ void xchg_ack_kernel(XchgParams q) {
+  const int P = q.nranks, me = q.rank;
+  const unsigned long long e = ld_volatile_sys(q.flags[me] + 2 * P);
+  if ((int)threadIdx.x < P && (int)threadIdx.x != me)
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(q.flags[threadIdx.x] + P + me), "l"(e) : "memory");
+}
+
+static XchgParams xchg_params(const hssb_matrix* H, const CallParams& cp) {
+  XchgParams q;
+  memset(&q, 0, sizeof(q));
+  for (int r = 0; r < H->n_shards; ++r) { q.z[r] = H->peer_z[r]; q.flags[r] = H->peer_flags[r]; }
+  q.rank = H->shard_rank; q.nranks = H->n_shards;
+  q.slot_off = H->xchg_zoff * (long long)cp.nrhs;
+  q.slot_elems = H->xchg_slot_rows * (long long)cp.nrhs;
+  return q;
+}
+
 // ------------------------------------------------------------------ launch ---
 static int launch_generic(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
   if (ph.ntasks == 0) return HSSB_OK;
@@ -686,8 +768,24 @@ static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
       hssb_matrix* H; cudaStream_t st; size_t i; bool on;
       ~Rec() { if (on) cudaEventRecord(H->prof_events[i], st); }
     } rec{H, st, pi, prof};
+    if (ph.kind == PH_XCHG_ACK) {
+      if (H->peer_xchg) {
+        xchg_ack_kernel<<<1, 32, 0, st>>>(xchg_params(H, cp));
+        H->launches++;
+        HSSB_CUDA(cudaGetLastError());
+      }
+      continue;
+    }
+    if (ph.kind == PH_EXCHANGE && H->peer_xchg) {
+      const XchgParams q = xchg_params(H, cp);
+      const int grid = (int)std::max<long long>(1, std::min<long long>(8, q.slot_elems / 2 / 256));
+      xchg_push_kernel<<<grid, 256, 0, st>>>(q);
+      H->launches++;
+      HSSB_CUDA(cudaGetLastError());
+      continue;
+    }
     if (ph.kind == PH_EXCHANGE) {
-      if (!H->nccl_comm) HSSB_FAIL(HSSB_ERR_STATE, "sharded matrix: call hssb_comm_init before hssb_matmul");
+      if (!H->nccl_comm) HSSB_FAIL(HSSB_ERR_STATE, "sharded matrix: call hssb_comm_init (or hssb_xchg_import) before hssb_matmul");
       double* buf = cp.Z + H->xchg_zoff * (int64_t)cp.nrhs;
       const size_t count = (size_t)H->xchg_slot_rows * (size_t)cp.nrhs;
       HSSB_NCCL(g_nccl.AllGather(buf + (size_t)H->shard_rank * count, buf, count, /*ncclDouble*/ 8, H->nccl_comm, st));
@@ -892,6 +990,12 @@ int hssb_destroy(hssb_matrix* h) {
   free_fast(h);
   for (auto e : h->prof_events) cudaEventDestroy(e);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
+  for (int r = 0; r < hssb_matrix::MAX_PEERS; ++r)
+    if (h->peer_xchg && r != h->shard_rank && r < h->n_shards) {
+      if (h->peer_z[r]) cudaIpcCloseMemHandle(h->peer_z[r]);
+      if (h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
+    }
+  cudaFree(h->my_flags);
   cudaFree(h->pool_dev);
   cudaFree(h->tasks_dev);
   cudaFree(h->z_dev);
@@ -1159,6 +1263,48 @@ int hssb_comm_init(hssb_matrix* h, const void* id128, int rank, int n_ranks) {
   return HSSB_OK;
 }
 
+
+int hssb_xchg_export(hssb_matrix* h, void* out128) {
+  if (!h || !out128) HSSB_FAIL(HSSB_ERR_ARG, "hssb_xchg_export: NULL argument");
+  if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle has no device");
+  if (h->n_shards < 2 || h->n_shards > hssb_matrix::MAX_PEERS) HSSB_FAIL(HSSB_ERR_STATE, "hssb_xchg_export: needs 2..16 shards");
+  if (!h->z_dev) HSSB_FAIL(HSSB_ERR_STATE, "hssb_xchg_export: call hssb_reserve(max_nrhs) first");
+  DeviceGuard dg(h->device);
+  if (!h->my_flags) {
+    HSSB_CUDA(cudaMalloc(&h->my_flags, 64 * sizeof(unsigned long long)));
+    HSSB_CUDA(cudaMemset(h->my_flags, 0, 64 * sizeof(unsigned long long)));
+    HSSB_CUDA(cudaDeviceSynchronize());
+  }
+  cudaIpcMemHandle_t hz, hf;
+  HSSB_CUDA(cudaIpcGetMemHandle(&hz, h->z_dev));
+  HSSB_CUDA(cudaIpcGetMemHandle(&hf, h->my_flags));
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  memcpy(out128, &hz, 64);
+  memcpy((char*)out128 + 64, &hf, 64);
+  h->xchg_exported = true;
+  return HSSB_OK;
+}
+
+int hssb_xchg_import(hssb_matrix* h, const void* all_handles, int n_ranks) {
+  if (!h || !all_handles) HSSB_FAIL(HSSB_ERR_ARG, "hssb_xchg_import: NULL argument");
+  if (n_ranks != h->n_shards) HSSB_FAIL(HSSB_ERR_ARG, "hssb_xchg_import: %d handles for %d shards", n_ranks, h->n_shards);
+  if (!h->xchg_exported) HSSB_FAIL(HSSB_ERR_STATE, "hssb_xchg_import: call hssb_xchg_export first");
+  DeviceGuard dg(h->device);
+  for (int r = 0; r < n_ranks; ++r) {
+    if (r == h->shard_rank) { h->peer_z[r] = h->z_dev; h->peer_flags[r] = h->my_flags; continue; }
+    cudaIpcMemHandle_t hz, hf;
+    memcpy(&hz, (const char*)all_handles + 128 * r, 64);
+    memcpy(&hf, (const char*)all_handles + 128 * r + 64, 64);
+    void *pz = nullptr, *pf = nullptr;
+    HSSB_CUDA(cudaIpcOpenMemHandle(&pz, hz, cudaIpcMemLazyEnablePeerAccess));
+    HSSB_CUDA(cudaIpcOpenMemHandle(&pf, hf, cudaIpcMemLazyEnablePeerAccess));
+    h->peer_z[r] = (double*)pz;
+    h->peer_flags[r] = (unsigned long long*)pf;
+  }
+  h->peer_xchg = true;
+  invalidate_graphs(h);
+  return HSSB_OK;
+}
 
 // ---- test hooks: host-only planning (no device required) --------------------
 int hssb_plan_only(hssb_builder* b, int64_t root, int shard_rank, int n_shards, hssb_matrix** out) {

@@ -87,7 +87,7 @@ struct Node {
   int32_t ldz = 0, ldf = 0;
 };
 
-enum PhaseKind : int { PH_LEAF_UP = 0, PH_MERGE, PH_EXCHANGE, PH_TRANSLATE, PH_LEAF_DOWN };
+enum PhaseKind : int { PH_LEAF_UP = 0, PH_MERGE, PH_EXCHANGE, PH_TRANSLATE, PH_LEAF_DOWN, PH_XCHG_ACK };
 
 struct Phase {
   int kind;
@@ -137,6 +137,14 @@ struct hssb_matrix {
   // exchange
   int64_t xchg_zoff = -1, xchg_slot_rows = 0;  // all-gather buffer = P slots of slot_rows x nrhs
   void* nccl_comm = nullptr;
+  // peer-memory exchange (hssb_xchg_export / hssb_xchg_import): every rank maps the Z workspace and
+  // the flag block of every other rank (CUDA IPC) and pushes its subtree-root Z block over NVLink
+  static constexpr int MAX_PEERS = 16;
+  bool peer_xchg = false;
+  bool xchg_exported = false;
+  double* peer_z[MAX_PEERS] = {};
+  unsigned long long* peer_flags[MAX_PEERS] = {};  // [0,P): data flags, [P,2P): ack flags, [2P]: epoch, [2P+1]: ticket
+  unsigned long long* my_flags = nullptr;
   // options
   bool force_generic = false, use_graph = false, fused_leaf = false, profile = false;
   int debug_mode = 0;

@@ -185,6 +185,14 @@ int hssb_phase_time(hssb_matrix* h, int i, hssb_phase_time_t* out);
 int hssb_comm_unique_id(void* id128);
 int hssb_comm_init(hssb_matrix* h, const void* id128, int rank, int n_ranks);
 
+/* Peer-memory exchange (preferred on NVLink/NVSwitch boxes): instead of NCCL, every rank maps the
+ * exchange buffers of all peers through CUDA IPC and the subtree-root Z blocks are pushed with
+ * NVLink peer stores from inside the level schedule (one small kernel, graph-replayable).
+ * Call hssb_reserve(max_nrhs) first, then hssb_xchg_export on every rank, all-gather the 128-byte
+ * blobs by any means (rank order), then hssb_xchg_import on every rank.                          */
+int hssb_xchg_export(hssb_matrix* h, void* handle128);
+int hssb_xchg_import(hssb_matrix* h, const void* all_handles, int n_ranks);
+
 /* ---- measurement helpers (used by bench.py; not on the product path) --- */
 /* kind 0: FP64 FMA (DFMA) register-resident peak, kind 1: FP64 tensor (DMMA
  * m8n8k4) peak, returns TFLOP/s.  kind 2: device copy bandwidth over `bytes`
