@@ -109,11 +109,11 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 #ifndef HSSB_DOWN_WARPS
 #define HSSB_DOWN_WARPS 8
 #endif
-template <int M, int R, bool DOWN>
+template <int M, int R, bool DOWN, int NT_>
 struct StreamCfg {
   static constexpr int MO = DOWN ? M : R;
   static constexpr int K0 = M, K1 = DOWN ? R : 0;
-  static constexpr int NT = DOWN ? 8192 / M : (M >= 256 ? 32 : 64);  // same tile as leaf-down so both share X tiles
+  static constexpr int NT = NT_;  // right-hand sides per tile: 8192 / M, or 32 for M = 128 when nrhs <= 32
   static constexpr int NWARPS = DOWN ? HSSB_DOWN_WARPS : 8;           // consumer warps (one extra warp produces)
   static constexpr int WR = DOWN ? M / 32 : ((R >= 32 ? 2 : 1) > 64 / NT ? (R >= 32 ? 2 : 1) : 64 / NT);  // warps along OUT rows
   static constexpr int WC = NWARPS / WR;                             // warps along right-hand sides
@@ -124,7 +124,7 @@ struct StreamCfg {
   static constexpr int LDF = K1 + 4, LDA = MO + 4;
   static constexpr int XSLABS = K0 / 16;                 // X block = XSLABS boxes of {16 rows x NT cols}, 128B-swizzled
   static constexpr int XBUF = K0 * NT;                   // doubles per X buffer (dense)
-  static constexpr int BAR_BYTES = 128;
+  static constexpr int BAR_BYTES = 256;
   static constexpr int FIXED_BYTES = BAR_BYTES + 8 * (2 * XBUF + (K1 ? NT * LDF : 0));
   static constexpr int STAGE_BYTES = 8 * KC * LDA;
   static constexpr int FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
@@ -141,10 +141,10 @@ struct StreamCfg {
   static_assert(SMEM <= 232448 && 2 * NSTAGE + 6 <= BAR_BYTES / 8, "shared memory budget");
 };
 
-template <int M, int R, bool DOWN>
-__global__ void __launch_bounds__(StreamCfg<M, R, DOWN>::NWARPS * 32 + 32, 1)
+template <int M, int R, bool DOWN, int NT_>
+__global__ void __launch_bounds__(StreamCfg<M, R, DOWN, NT_>::NWARPS * 32 + 32, 1)
 stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p, const __grid_constant__ CUtensorMap xmap) {
-  using C = StreamCfg<M, R, DOWN>;
+  using C = StreamCfg<M, R, DOWN, NT_>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   // X buffers first: the 128-byte swizzle needs 1024-byte aligned boxes
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + C::SMEM - C::BAR_BYTES);
@@ -386,11 +386,11 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
 // A0/A1 are padded pool blocks (one bulk copy each) streamed through a ring; B0/B1 are padded
 // workspace tiles (one bulk copy each), double buffered per item.  Consecutive tiles of one task
 // re-read A0/A1 from L2.  Same producer / consumer protocol as the leaf kernel.
-template <int R>
+template <int R, int NT_>
 struct NodeCfg {
-  static constexpr int NT = 64;
+  static constexpr int NT = NT_;                        // 64, or 32 when nrhs <= 32 (no half-empty tiles)
   static constexpr int LD = R + 4;
-  static constexpr int WR = R >= 32 ? 2 : 1, WC = 8 / WR;
+  static constexpr int WR = (R >= 32 || NT < 64) ? 2 : 1, WC = 8 / WR;
   static constexpr int TM = R / WR / 8, TN = NT / WC / 8;
   static constexpr int KSTEPS = R / 4;
   static constexpr int TILE = NT * LD;                 // doubles per B tile
@@ -404,11 +404,11 @@ struct NodeCfg {
   static_assert(NSTAGE >= 2 && TM >= 1 && TN >= 1 && 2 * NSTAGE + 4 <= BAR_BYTES / 8, "node kernel configuration");
 };
 
-template <int R>
-__global__ void __launch_bounds__(288, NodeCfg<R>::CTAS_PER_SM)
+template <int R, int NT_>
+__global__ void __launch_bounds__(288, NodeCfg<R, NT_>::CTAS_PER_SM)
 stream_node_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p) {
-  using C = NodeCfg<R>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  using C = NodeCfg<R, NT_>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
   double* Bt = reinterpret_cast<double*>(smem_raw);            // [2 buffers][2 operands][NT][LD]
   double* As = Bt + 4 * C::TILE;                               // [NSTAGE][R][LD]
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + C::SMEM - C::BAR_BYTES);
@@ -560,25 +560,39 @@ static int make_x_map(CUtensorMap* map, const double* X, int64_t rows, int64_t n
   return HSSB_OK;
 }
 
-template <int M, int R>
-static int launch_leaf(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st, bool down) {
+template <int M, int R, bool DOWN, int NT>
+static int launch_leaf_nt(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
+  using C = StreamCfg<M, R, DOWN, NT>;
   FastState* fs = (FastState*)H->fast_state;
   CUtensorMap xmap;
-  if (down) {
-    using C = StreamCfg<M, R, true>;
-    const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
-    const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
-    if (int rc = make_x_map(&xmap, cp.X, H->local_n, cp.nrhs, cp.ldx, C::NT)) return rc;
-    if (int rc = fs->configure((const void*)stream_leaf_kernel<M, R, true>, C::SMEM)) return rc;
-    stream_leaf_kernel<M, R, true><<<grid, C::NWARPS * 32 + 32, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp, xmap);
-  } else {
-    using C = StreamCfg<M, R, false>;
-    const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
-    const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
-    if (int rc = make_x_map(&xmap, cp.X, H->local_n, cp.nrhs, cp.ldx, C::NT)) return rc;
-    if (int rc = fs->configure((const void*)stream_leaf_kernel<M, R, false>, C::SMEM)) return rc;
-    stream_leaf_kernel<M, R, false><<<grid, C::NWARPS * 32 + 32, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp, xmap);
-  }
+  const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
+  const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
+  if (int rc = make_x_map(&xmap, cp.X, H->local_n, cp.nrhs, cp.ldx, C::NT)) return rc;
+  if (int rc = fs->configure((const void*)stream_leaf_kernel<M, R, DOWN, NT>, C::SMEM)) return rc;
+  stream_leaf_kernel<M, R, DOWN, NT><<<grid, C::NWARPS * 32 + 32, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp, xmap);
+  H->launches++;
+  HSSB_CUDA(cudaGetLastError());
+  return HSSB_OK;
+}
+
+template <int M, int R>
+static int launch_leaf(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st, bool down) {
+  constexpr int NTW = 8192 / M;  // widest tile: 64 right-hand sides for 128-row leaves, 32 for 256-row leaves
+  // with 64-wide tiles a last (or only) tile of <= 32 columns would waste half of the DMMA work
+  const int rem = cp.nrhs % 64;
+  const bool narrow = NTW > 32 && rem > 0 && rem <= 32 && cp.nrhs < 128;
+  if (narrow) return down ? launch_leaf_nt<M, R, true, 32>(H, ph, cp, st) : launch_leaf_nt<M, R, false, 32>(H, ph, cp, st);
+  return down ? launch_leaf_nt<M, R, true, NTW>(H, ph, cp, st) : launch_leaf_nt<M, R, false, NTW>(H, ph, cp, st);
+}
+
+template <int R, int NT>
+static int launch_node_nt(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
+  using C = NodeCfg<R, NT>;
+  FastState* fs = (FastState*)H->fast_state;
+  const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
+  const int grid = (int)std::min<int64_t>(ph.ntasks * ntiles, (int64_t)fs->num_sms * C::CTAS_PER_SM);
+  if (int rc = fs->configure((const void*)stream_node_kernel<R, NT>, C::SMEM)) return rc;
+  stream_node_kernel<R, NT><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
   return HSSB_OK;
@@ -586,15 +600,10 @@ static int launch_leaf(hssb_matrix* H, const Phase& ph, const CallParams& cp, cu
 
 template <int R>
 static int launch_node(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
-  using C = NodeCfg<R>;
-  FastState* fs = (FastState*)H->fast_state;
-  const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
-  const int grid = (int)std::min<int64_t>(ph.ntasks * ntiles, (int64_t)fs->num_sms * C::CTAS_PER_SM);
-  if (int rc = fs->configure((const void*)stream_node_kernel<R>, C::SMEM)) return rc;
-  stream_node_kernel<R><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
-  H->launches++;
-  HSSB_CUDA(cudaGetLastError());
-  return HSSB_OK;
+  // the last (or only) column tile is at most half full with 64-wide tiles: use 32-wide ones
+  const int rem = cp.nrhs % 64;
+  if (rem > 0 && rem <= 32 && cp.nrhs < 128) return launch_node_nt<R, 32>(H, ph, cp, st);
+  return launch_node_nt<R, 64>(H, ph, cp, st);
 }
 
 static bool fast_shape_supported(int64_t m, int64_t r) {
