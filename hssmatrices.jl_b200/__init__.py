@@ -64,7 +64,7 @@ class _PhaseTime(C.Structure):
 
 class _PhaseT(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
-        "kind", "task0", "ntasks", "maxM", "level", "top", "fast", "xchg_zoff", "xchg_slot_rows")]
+        "kind", "task0", "ntasks", "maxM", "level", "top", "fast", "xchg_zoff", "xchg_slot_rows", "transposed")]
 
 
 _lib = None
@@ -92,6 +92,8 @@ SIGNATURES = {
     "hssb_reserve": (C.c_int, [_P, _i64]),
     "hssb_matmul": (C.c_int, [_P, _i64, _i64, _i64, _P, _i64, _P, _i64, C.c_double, C.c_double]),
     "hssb_matmul_dev": (C.c_int, [_P, _i64, _i64, _i64, _P, _i64, _P, _i64, C.c_double, C.c_double, _P]),
+    "hssb_matmul_t": (C.c_int, [_P, _i64, _i64, _i64, _P, _i64, _P, _i64, C.c_double, C.c_double]),
+    "hssb_matmul_t_dev": (C.c_int, [_P, _i64, _i64, _i64, _P, _i64, _P, _i64, C.c_double, C.c_double, _P]),
     "hssb_sync": (C.c_int, [_P]),
     "hssb_set_option": (C.c_int, [_P, C.c_int, _i64]),
     "hssb_get_option": (_i64, [_P, C.c_int]),
@@ -269,6 +271,14 @@ class HssMatrix:
         self._packed = pack(self, device=device)
         return self._packed
 
+    def __rmatmul__(self, A):
+        """`*(A::AbstractMatrix, hssB)` (src/matmul.jl:14) without the reference's adjoint copy."""
+        if self._packed is None:
+            self.repack()
+        return self._packed.__rmatmul__(A)
+
+    __array_priority__ = 1000  # let `ndarray @ HssMatrix` reach __rmatmul__
+
     def __matmul__(self, B):
         """`*(hssA, B)` (src/matmul.jl:13) and `*(hssA, x::Vector)` (:15)."""
         B = _f64(B)
@@ -407,6 +417,8 @@ def synthetic(n, leafsize, rank, seed, device=0, shard_rank=0, n_shards=1, plan_
 class PackedHss:
     """Handle to a packed, device-resident HSS matrix (hssb_matrix*)."""
 
+    __array_priority__ = 1000  # let `ndarray @ PackedHss` reach __rmatmul__
+
     def __init__(self, handle):
         self._h = handle
         self.info = _Info()
@@ -504,9 +516,9 @@ class PackedHss:
         return 8 * (self.info.gen_elems + self.info.local_n * nrhs + self.info.local_m * nrhs * (2 if beta_nonzero else 1))
 
     # the product -------------------------------------------------------------
-    def mul_(self, Cm, B, alpha=1.0, beta=0.0):
+    def mul_(self, Cm, B, alpha=1.0, beta=0.0, trans=False):
         """mul!(C, hssA, B, alpha, beta) with host (numpy) arrays; C must be
-        column-major (Julia layout) and is updated in place."""
+        column-major (Julia layout) and is updated in place.  trans=True applies A'."""
         B = np.asarray(B, dtype=np.float64)
         if B.ndim != 2 or Cm.ndim != 2:
             raise DimensionMismatch("B and C must be matrices")
@@ -515,9 +527,23 @@ class PackedHss:
         if Cm.shape[1] != B.shape[1]:  # matmul.jl:20
             raise DimensionMismatch("Dimensions of C don't match up with A and B.")
         Bf = _fcol(B)
-        _check(lib().hssb_matmul(self._h, Cm.shape[0], Bf.shape[0], Bf.shape[1], _ptr(Bf), max(Bf.shape[0], 1),
-                                 _ptr(Cm), max(Cm.shape[0], 1), float(alpha), float(beta)))
+        fn = lib().hssb_matmul_t if trans else lib().hssb_matmul
+        _check(fn(self._h, Cm.shape[0], Bf.shape[0], Bf.shape[1], _ptr(Bf), max(Bf.shape[0], 1),
+                  _ptr(Cm), max(Cm.shape[0], 1), float(alpha), float(beta)))
         return Cm
+
+    def tmatmul(self, B):
+        """A' * B on the same packed generators (no adjoint copy, cf. hssmatrix.jl:165-171)."""
+        B = _f64(B)
+        if B.ndim == 1:
+            return self.tmatmul(B.reshape(-1, 1)).reshape(-1)
+        Cm = np.empty((self.info.local_n, B.shape[1]), order="F")
+        return self.mul_(Cm, B, 1.0, 0.0, trans=True)
+
+    def __rmatmul__(self, A):
+        """`*(A::AbstractMatrix, hssB)` (src/matmul.jl:14): A*hssB = (hssB' * A')'."""
+        A = _f64(A)
+        return self.tmatmul(np.asfortranarray(A.T)).T
 
     def __matmul__(self, B):
         B = _f64(B)

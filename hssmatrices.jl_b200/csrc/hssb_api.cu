@@ -252,16 +252,94 @@ static void layout_workspace(hssb_matrix* H) {
   H->f_rows = std::max<int64_t>(fo, 2);
 }
 
-static void add_phase(hssb_matrix* H, int kind, int level, bool top, std::vector<GTask>& batch) {
+static void add_phase(hssb_matrix* H, int kind, int level, bool top, std::vector<GTask>& batch,
+                      std::vector<Phase>* dst = nullptr) {
   if (batch.empty()) return;
   Phase ph;
   ph.kind = kind; ph.level = level; ph.top = top;
   ph.task0 = (int64_t)H->tasks_host.size();
   ph.ntasks = (int64_t)batch.size();
-  for (auto& t : batch) { ph.maxM = std::max(ph.maxM, t.M); H->flops_per_rhs += 2ll * t.M * ((int64_t)t.K0 + t.K1); }
+  for (auto& t : batch) {
+    ph.maxM = std::max(ph.maxM, t.M);
+    if (!dst) H->flops_per_rhs += 2ll * t.M * ((int64_t)t.K0 + t.K1);
+  }
   H->tasks_host.insert(H->tasks_host.end(), batch.begin(), batch.end());
-  H->phases.push_back(ph);
+  (dst ? *dst : H->phases).push_back(ph);
   batch.clear();
+}
+
+// Task table of Y = A' X on the SAME packed generators (`*(A, hssB)`,
+// src/matmul.jl:14, which in the reference copies the whole adjoint tree, hssmatrix.jl:165-171,
+// on every call).  The adjoint swaps roles: U <-> V, R <-> W, B12 <-> B21', D -> D'; every stored
+// block is therefore applied transposed (ta = 1, the any-shape kernel), the "Z" blocks of the
+// adjoint have kr rows and live in the F workspace, its "F" blocks have kw rows and live in Z.
+// Single shard only.
+static void build_plan_transposed(hssb_matrix* H) {
+  auto& nodes = H->nodes;
+  if (H->n_shards != 1) return;
+  std::vector<GTask> batch;
+  auto blank = []() { GTask t; memset(&t, 0, sizeof(t)); t.lda0 = t.lda1 = t.ldb0 = t.ldb1 = t.ldc = 2; return t; };
+  auto& out = H->phases_t;
+  // leaf up: Z' = U' X[rows]
+  for (int64_t li : H->leaves) {
+    const Node& t = nodes[(size_t)li];
+    if (t.parent < 0 || t.kr == 0) continue;
+    GTask g = blank();
+    g.a0 = t.off[BK_U]; g.lda0 = t.ld[BK_U]; g.ta0 = 1; g.sb0 = SRC_X; g.b0 = t.row0; g.K0 = (int32_t)t.m;
+    g.M = (int32_t)t.kr; g.sc = SRC_F; g.c = t.foff; g.ldc = t.ldf;
+    batch.push_back(g);
+  }
+  add_phase(H, PH_LEAF_UP, 0, false, batch, &out);
+  // merges: Z' = R1' Z1' + R2' Z2'
+  for (int h = 1; h <= nodes[0].height; ++h) {
+    for (auto& t : nodes) {
+      if (t.leaf || t.height != h || t.parent < 0 || t.kr == 0) continue;
+      const Node& l = nodes[(size_t)t.left];
+      const Node& r = nodes[(size_t)t.right];
+      GTask g = blank();
+      g.a0 = l.off[BK_R]; g.lda0 = l.ld[BK_R]; g.ta0 = 1; g.sb0 = SRC_F; g.b0 = l.foff; g.ldb0 = l.ldf; g.K0 = (int32_t)l.kr;
+      g.a1 = r.off[BK_R]; g.lda1 = r.ld[BK_R]; g.ta1 = 1; g.sb1 = SRC_F; g.b1 = r.foff; g.ldb1 = r.ldf; g.K1 = (int32_t)r.kr;
+      if (g.a0 < 0) g.K0 = 0;
+      if (g.a1 < 0) g.K1 = 0;
+      g.M = (int32_t)t.kr; g.sc = SRC_F; g.c = t.foff; g.ldc = t.ldf;
+      batch.push_back(g);
+    }
+    add_phase(H, PH_MERGE, h, false, batch, &out);
+  }
+  // translates: F1' = B21' Z2' (+ W1 F'), F2' = B12' Z1' (+ W2 F')   (the pool holds W', so W = (W')')
+  for (int d = 0; d <= (int)H->depth; ++d) {
+    for (auto& t : nodes) {
+      if (t.leaf || t.depth != d) continue;
+      const Node& l = nodes[(size_t)t.left];
+      const Node& r = nodes[(size_t)t.right];
+      const bool has_f = t.parent >= 0 && t.kw > 0;
+      for (int side = 0; side < 2; ++side) {
+        const Node& c = side ? r : l;
+        const Node& sb = side ? l : r;
+        if (c.kw == 0) continue;
+        GTask g = blank();
+        const int bk = side ? BK_B12 : BK_B21;  // B21 is kr(r) x kw(l): B21' maps Z'(r) to F'(l)
+        g.a0 = t.off[bk]; g.lda0 = t.ld[bk]; g.ta0 = 1; g.sb0 = SRC_F; g.b0 = sb.foff; g.ldb0 = sb.ldf; g.K0 = (int32_t)sb.kr;
+        if (has_f) { g.a1 = c.off[BK_W]; g.lda1 = c.ld[BK_W]; g.ta1 = 1; g.sb1 = SRC_Z; g.b1 = t.zoff; g.ldb1 = t.ldz; g.K1 = (int32_t)t.kw; }
+        if (g.a0 < 0) g.K0 = 0;
+        if (g.a1 < 0) g.K1 = 0;
+        g.M = (int32_t)c.kw; g.sc = SRC_Z; g.c = c.zoff; g.ldc = c.ldz;
+        batch.push_back(g);
+      }
+    }
+    add_phase(H, PH_TRANSLATE, d, false, batch, &out);
+  }
+  // leaf down: Y[cols] = alpha (D' X[rows] + V F') + beta Y   (the pool holds V')
+  for (int64_t li : H->leaves) {
+    const Node& t = nodes[(size_t)li];
+    GTask g = blank();
+    g.a0 = t.off[BK_D]; g.lda0 = t.ld[BK_D]; g.ta0 = 1; g.sb0 = SRC_X; g.b0 = t.row0; g.K0 = (int32_t)t.m;
+    if (t.parent >= 0 && t.kw > 0) { g.a1 = t.off[BK_V]; g.lda1 = t.ld[BK_V]; g.ta1 = 1; g.sb1 = SRC_Z; g.b1 = t.zoff; g.ldb1 = t.ldz; g.K1 = (int32_t)t.kw; }
+    if (g.a0 < 0) g.K0 = 0;
+    g.M = (int32_t)t.n; g.sc = SRC_Y; g.c = t.col0; g.epilogue = 1;
+    if (g.M > 0) batch.push_back(g);
+  }
+  add_phase(H, PH_LEAF_DOWN, 0, false, batch, &out);
 }
 
 static void build_plan(hssb_matrix* H) {
@@ -417,6 +495,7 @@ static int plan_matrix(hssb_matrix* H) {
   layout_workspace(H);
   build_plan(H);
   plan_fast_phases(H);
+  build_plan_transposed(H);
 
   return HSSB_OK;
 }
@@ -751,7 +830,8 @@ static int launch_generic(hssb_matrix* H, const Phase& ph, const CallParams& cp,
 }
 
 static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
-  const bool prof = H->profile;
+  const std::vector<Phase>& phases = cp.trans ? H->phases_t : H->phases;
+  const bool prof = H->profile && !cp.trans;
   if (prof) {
     while (H->prof_events.size() < H->phases.size() + 1) {
       cudaEvent_t e;
@@ -762,7 +842,7 @@ static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
     H->prof_nrhs = cp.nrhs;
   }
   size_t pi = 0;
-  for (const Phase& ph : H->phases) {
+  for (const Phase& ph : phases) {
     ++pi;
     struct Rec {
       hssb_matrix* H; cudaStream_t st; size_t i; bool on;
@@ -812,7 +892,7 @@ static void invalidate_graphs(hssb_matrix* H) {
 
 static bool same_call(const CallParams& a, const CallParams& b) {
   return a.pool == b.pool && a.X == b.X && a.Y == b.Y && a.Z == b.Z && a.F == b.F && a.ldx == b.ldx && a.ldy == b.ldy &&
-         a.nrhs == b.nrhs && a.alpha == b.alpha && a.beta == b.beta && a.debug == b.debug;
+         a.nrhs == b.nrhs && a.alpha == b.alpha && a.beta == b.beta && a.debug == b.debug && a.trans == b.trans;
 }
 
 static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
@@ -1071,16 +1151,18 @@ int hssb_reserve(hssb_matrix* h, int64_t max_nrhs) {
   return ensure_workspace(h, max_nrhs);
 }
 
-int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* dX, int64_t ldx,
-                    double* dY, int64_t ldy, double alpha, double beta, void* stream) {
+static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* dX, int64_t ldx,
+                           double* dY, int64_t ldy, double alpha, double beta, void* stream) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
-  // DimensionMismatch checks of matmul.jl:19-20
-  if (rows_x != h->local_n)
+  if (trans && h->n_shards != 1) HSSB_FAIL(HSSB_ERR_STATE, "the transposed product is not available on a sharded matrix");
+  // DimensionMismatch checks of matmul.jl:19-20 (for A' the roles of the two dimensions swap)
+  const int64_t need_x = trans ? h->local_m : h->local_n, need_y = trans ? h->local_n : h->local_m;
+  if (rows_x != need_x)
     HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: first dimension of B (%lld) does not match second dimension of A (%lld)",
-              (long long)rows_x, (long long)h->local_n);
-  if (rows_y != h->local_m)
+              (long long)rows_x, (long long)need_x);
+  if (rows_y != need_y)
     HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: dimensions of C (%lld rows) don't match up with A (%lld rows)",
-              (long long)rows_y, (long long)h->local_m);
+              (long long)rows_y, (long long)need_y);
   if (nrhs < 0 || nrhs > INT32_MAX) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: bad nrhs");
   if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle: hssb200 has no CPU fallback, the product needs a B200");
   if (nrhs == 0 || rows_y == 0) return HSSB_OK;
@@ -1093,22 +1175,24 @@ int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   CallParams cp;
   cp.pool = h->pool_dev; cp.X = dX; cp.Y = dY; cp.Z = h->z_dev; cp.F = h->f_dev;
-  cp.ldx = ldx; cp.ldy = ldy; cp.nrhs = (int32_t)nrhs; cp.alpha = alpha; cp.beta = beta; cp.debug = h->debug_mode;
+  cp.ldx = ldx; cp.ldy = ldy; cp.nrhs = (int32_t)nrhs; cp.alpha = alpha; cp.beta = beta; cp.debug = h->debug_mode; cp.trans = trans;
   // graph replay: always for the host entry (its staging pointers are stable), on request for
   // caller-owned device pointers (a new pointer set costs a capture + instantiate)
   if ((h->use_graph || h->in_host_call) && !h->profile) return run_graph(h, cp, st);
   return run_phases(h, cp, st);
 }
 
-int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx, double* Y,
-                int64_t ldy, double alpha, double beta) {
+static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx,
+                            double* Y, int64_t ldy, double alpha, double beta) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
-  if (rows_x != h->local_n)
+  if (trans && h->n_shards != 1) HSSB_FAIL(HSSB_ERR_STATE, "the transposed product is not available on a sharded matrix");
+  const int64_t need_x = trans ? h->local_m : h->local_n, need_y = trans ? h->local_n : h->local_m;
+  if (rows_x != need_x)
     HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: first dimension of B (%lld) does not match second dimension of A (%lld)",
-              (long long)rows_x, (long long)h->local_n);
-  if (rows_y != h->local_m)
+              (long long)rows_x, (long long)need_x);
+  if (rows_y != need_y)
     HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: dimensions of C (%lld rows) don't match up with A (%lld rows)",
-              (long long)rows_y, (long long)h->local_m);
+              (long long)rows_y, (long long)need_y);
   if (nrhs < 0 || nrhs > INT32_MAX) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: bad nrhs");
   if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle: hssb200 has no CPU fallback, the product needs a B200");
   if (nrhs == 0 || rows_y == 0) return HSSB_OK;
@@ -1119,7 +1203,8 @@ int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, co
   if (nrhs > h->stage_nrhs) {
     cudaFree(h->x_stage); cudaFree(h->y_stage);
     h->x_stage = h->y_stage = nullptr; h->stage_nrhs = 0;
-    const size_t xb = (size_t)std::max<int64_t>(h->local_n, 1) * (size_t)nrhs * 8, yb = (size_t)h->local_m * (size_t)nrhs * 8;
+    const size_t rmax = (size_t)std::max<int64_t>(std::max(h->local_n, h->local_m), 1);  // either stage may hold X or Y (A or A')
+    const size_t xb = rmax * (size_t)nrhs * 8, yb = rmax * (size_t)nrhs * 8;
     if (cudaMalloc(&h->x_stage, xb) != cudaSuccess || cudaMalloc(&h->y_stage, yb) != cudaSuccess) {
       cudaGetLastError();
       HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of X/Y staging (%.3f GB) failed", (xb + yb) * 1e-9);
@@ -1127,7 +1212,7 @@ int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, co
     h->stage_nrhs = nrhs;
     invalidate_graphs(h);
   }
-  const int64_t sx = std::max<int64_t>(h->local_n, 1), sy = h->local_m;
+  const int64_t sx = std::max<int64_t>(rows_x, 1), sy = rows_y;
   // The product is independent per right-hand side, so the call is pipelined over column blocks:
   // H2D of block j+1 (copy-in stream), the product of block j (compute stream) and D2H of block
   // j-1 (copy-out stream) overlap; PCIe is full duplex.  Blocks are a multiple of the widest
@@ -1162,7 +1247,7 @@ int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, co
     const int64_t c0 = j * cb, nc = std::min(cb, nrhs - c0);
     HSSB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[j], 0));
     h->in_host_call = true;
-    int rc = hssb_matmul_dev(h, rows_y, rows_x, nc, h->x_stage + c0 * sx, sx, h->y_stage + c0 * sy, sy, alpha, beta, h->stream);
+    int rc = matmul_dev_impl(h, trans, rows_y, rows_x, nc, h->x_stage + c0 * sx, sx, h->y_stage + c0 * sy, sy, alpha, beta, h->stream);
     h->in_host_call = false;
     if (rc) { cudaStreamSynchronize(h->copy_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_out); return rc; }
     HSSB_CUDA(cudaEventRecord(h->ev_done[j], h->stream));
@@ -1173,6 +1258,26 @@ int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, co
   HSSB_CUDA(cudaStreamSynchronize(h->copy_out));
   HSSB_CUDA(cudaStreamSynchronize(h->stream));
   return HSSB_OK;
+}
+
+int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx, double* Y,
+                int64_t ldy, double alpha, double beta) {
+  return matmul_host_impl(h, 0, rows_y, rows_x, nrhs, X, ldx, Y, ldy, alpha, beta);
+}
+
+int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* dX, int64_t ldx, double* dY,
+                    int64_t ldy, double alpha, double beta, void* stream) {
+  return matmul_dev_impl(h, 0, rows_y, rows_x, nrhs, dX, ldx, dY, ldy, alpha, beta, stream);
+}
+
+int hssb_matmul_t(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx, double* Y,
+                  int64_t ldy, double alpha, double beta) {
+  return matmul_host_impl(h, 1, rows_y, rows_x, nrhs, X, ldx, Y, ldy, alpha, beta);
+}
+
+int hssb_matmul_t_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* dX, int64_t ldx, double* dY,
+                      int64_t ldy, double alpha, double beta, void* stream) {
+  return matmul_dev_impl(h, 1, rows_y, rows_x, nrhs, dX, ldx, dY, ldy, alpha, beta, stream);
 }
 
 int hssb_sync(hssb_matrix* h) {
@@ -1344,7 +1449,7 @@ int hssb_plan_only_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t
 int hssb_debug_counts(const hssb_matrix* h, int64_t* n_tasks, int64_t* n_phases, int64_t* pool_len) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_counts: NULL handle");
   if (n_tasks) *n_tasks = (int64_t)h->tasks_host.size();
-  if (n_phases) *n_phases = (int64_t)h->phases.size();
+  if (n_phases) *n_phases = (int64_t)h->phases.size() + (int64_t)h->phases_t.size();  // transposed plan follows
   if (pool_len) *pool_len = h->pool_len;
   return HSSB_OK;
 }
@@ -1360,10 +1465,11 @@ int hssb_debug_task(const hssb_matrix* h, int64_t i, hssb_task_t* o) {
 }
 
 int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* o) {
-  if (!h || !o || i < 0 || i >= (int64_t)h->phases.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_phase: bad argument");
-  const Phase& p = h->phases[(size_t)i];
+  if (!h || !o || i < 0 || i >= (int64_t)(h->phases.size() + h->phases_t.size())) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_phase: bad argument");
+  const bool tr = i >= (int64_t)h->phases.size();
+  const Phase& p = tr ? h->phases_t[(size_t)i - h->phases.size()] : h->phases[(size_t)i];
   o->kind = p.kind; o->task0 = p.task0; o->ntasks = p.ntasks; o->maxM = p.maxM; o->level = p.level;
-  o->top = p.top; o->fast = p.fast;
+  o->top = p.top; o->fast = p.fast; o->transposed = tr;
   o->xchg_zoff = h->xchg_zoff; o->xchg_slot_rows = h->xchg_slot_rows;
   return HSSB_OK;
 }

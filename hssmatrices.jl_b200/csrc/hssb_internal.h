@@ -61,6 +61,7 @@ struct CallParams {
   int64_t ldx, ldy;
   int32_t nrhs;
   double alpha, beta;
+  int32_t trans;  // 1: Y = A' X (transposed plan)
   int32_t debug;  // HSSB_OPT_DEBUG bits: 1 = leaf kernels compute without waiting for data, 2 = move data without computing
 };
 
@@ -107,6 +108,7 @@ struct hssb_matrix {
   std::vector<hssb::Node> nodes;  // BFS order, root = 0
   std::vector<int64_t> leaves;    // local leaves, left to right
   std::vector<hssb::Phase> phases;
+  std::vector<hssb::Phase> phases_t;  // Y = A' X on the same generators (single shard)
   std::vector<hssb::GTask> tasks_host;
   hssb::GTask* tasks_dev = nullptr;
   double* pool_dev = nullptr;

@@ -148,6 +148,16 @@ int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
 int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
                     const double* dX, int64_t ldx, double* dY, int64_t ldy, double alpha, double beta,
                     void* stream);
+/* Transposed product Y = alpha * A' * X + beta * Y on the SAME packed generators: what
+ * `*(A::AbstractMatrix, hssB)` (matmul.jl:14) and `hssA' * X` need.  The reference builds a full
+ * copied adjoint HssMatrix (hssmatrix.jl:165-171) on every such call; here the adjoint is a second
+ * task table over the same pool.  rows_x must be size(A,1), rows_y size(A,2).  Single shard only;
+ * runs on the any-shape kernel.                                                                   */
+int hssb_matmul_t(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
+                  const double* X, int64_t ldx, double* Y, int64_t ldy, double alpha, double beta);
+int hssb_matmul_t_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
+                      const double* dX, int64_t ldx, double* dY, int64_t ldy, double alpha, double beta,
+                      void* stream);
 int hssb_sync(hssb_matrix* h);
 
 /* Options. */
@@ -214,6 +224,7 @@ typedef struct hssb_phase_t {
   int64_t kind; /* 0 leaf-up, 1 merge, 2 exchange, 3 translate, 4 leaf-down */
   int64_t task0, ntasks, maxM, level, top, fast;
   int64_t xchg_zoff, xchg_slot_rows;
+  int64_t transposed; /* 1: belongs to the plan of hssb_matmul_t (listed after the forward plan) */
 } hssb_phase_t;
 int hssb_plan_only(hssb_builder* b, int64_t root, int shard_rank, int n_shards, hssb_matrix** out);
 int hssb_plan_only_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, int shard_rank,

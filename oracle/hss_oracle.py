@@ -75,6 +75,10 @@ def _bisection_cluster(lo, hi, leafsize):
     return node
 
 
+def nleaves_cl(cl):
+    return 1 if cl.isleaf() else nleaves_cl(cl.left) + nleaves_cl(cl.right)
+
+
 def leaves(cl):
     if cl.isleaf():
         return [cl.data]

@@ -59,10 +59,12 @@ class ShardState:
             self.run_task(self.tasks[i], alpha, beta)
 
 
-def run_plan(packed, X, Y, alpha=1.0, beta=0.0):
-    """Single-shard plan: Y (in place) = alpha*A*X + beta*Y."""
+def run_plan(packed, X, Y, alpha=1.0, beta=0.0, trans=False):
+    """Single-shard plan: Y (in place) = alpha*op(A)*X + beta*Y, op(A) = A' if trans."""
     st = ShardState(packed, X, Y, X.shape[1])
     for ph in st.phases:
+        if bool(ph.transposed) != bool(trans):
+            continue
         assert ph.kind != PH_EXCHANGE
         st.run_phase(ph, alpha, beta)
     return Y
@@ -73,6 +75,8 @@ def run_sharded(packs, Xs, Ys, alpha=1.0, beta=0.0):
     own slot of the exchange buffer."""
     nrhs = Xs[0].shape[1]
     sts = [ShardState(p, x, y, nrhs) for p, x, y in zip(packs, Xs, Ys)]
+    for s in sts:
+        s.phases = [ph for ph in s.phases if not ph.transposed]
     nph = len(sts[0].phases)
     assert all(len(s.phases) == nph for s in sts)
     for i in range(nph):

@@ -70,6 +70,38 @@ def test_rectangular_unbalanced_subblock(gpu, oracle):
     assert relerr(to_product_tree(gpu, sub) @ Xs, oracle.matmul(sub, Xs)) <= TOL
 
 
+def test_transposed_product(gpu, oracle):
+    """`*(A::AbstractMatrix, hssB)` (matmul.jl:14) and hssA' * X without the adjoint copy of
+    hssmatrix.jl:165-171: second task table over the same packed generators."""
+    rng = np.random.default_rng(14)
+    rcl = oracle.bisection_cluster(500, 70)
+    ccl = oracle.bisection_cluster(333, 47)
+    h = oracle.random_hss(rcl, ccl, rng, 1, 7)
+    tree = to_product_tree(gpu, h)
+    X = rng.standard_normal((500, 6))
+    ref = oracle.matmul(oracle.adjoint(h), X)
+    P = tree.repack()
+    assert relerr(P.tmatmul(X), ref) <= TOL
+    A = rng.standard_normal((4, 500))
+    got = A @ tree                                   # matmul.jl:14
+    assert got.shape == (4, 333) and relerr(got, A @ oracle.full(h)) <= TOL
+    C0 = rng.standard_normal((333, 6))
+    got = P.mul_(np.asfortranarray(C0.copy()), X, -0.5, 3.0, trans=True)
+    assert relerr(got, -0.5 * ref + 3.0 * C0) <= TOL
+    with pytest.raises(gpu.DimensionMismatch):
+        P.tmatmul(np.zeros((333, 2)))
+    # forward product still right after a transposed one (the two plans share the workspaces)
+    Xf = rng.standard_normal((333, 3))
+    assert relerr(tree @ Xf, oracle.matmul(h, Xf)) <= TOL
+    # uniform synthetic tree (padded TMA-ready layout): transposed apply through the any-shape kernel
+    n, ls, r, seed = 2048, 128, 32, 9
+    hs = oracle.synthetic_hss(n, ls, r, seed)
+    Xs = rng.standard_normal((n, 5))
+    with gpu.synthetic(n, ls, r, seed) as Ps:
+        assert relerr(Ps.tmatmul(Xs), oracle.matmul(oracle.adjoint(hs), Xs)) <= TOL
+        assert relerr(Ps @ Xs, oracle.matmul(hs, Xs)) <= TOL
+
+
 def test_golden_fixtures(gpu, oracle):
     import make_golden
     gdir = os.path.join(os.path.dirname(__file__), "golden")

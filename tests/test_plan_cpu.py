@@ -82,6 +82,28 @@ def test_rectangular_and_unbalanced(hb, oracle):
     assert relerr(Y, ref) <= TOL
 
 
+@pytest.mark.parametrize("n,leafsize,nrhs,rmin,rmax", CASES[:5])
+def test_transposed_plan(hb, oracle, n, leafsize, nrhs, rmin, rmax):
+    """Y = A' X on the same packed generators == product with the reference's copied adjoint
+    (hssmatrix.jl:165-171), which is what `*(A, hssB)` (matmul.jl:14) computes."""
+    rng = np.random.default_rng(n + 1)
+    rcl = oracle.bisection_cluster(n, leafsize)
+    ccl = oracle.bisection_cluster(n + 7, leafsize + 3) if oracle.nleaves_cl(rcl) == oracle.nleaves_cl(oracle.bisection_cluster(n + 7, leafsize + 3)) else rcl
+    h = oracle.random_hss(rcl, ccl, rng, rmin, rmax)
+    m_, n_ = oracle.size(h)
+    X = rng.standard_normal((m_, nrhs))
+    ref = oracle.matmul(oracle.adjoint(h), X)
+    assert relerr(ref, oracle.full(h).T @ X) <= TOL
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    Y = np.full((n_, nrhs), np.nan, order="F")
+    plan_interp.run_plan(P, X, Y, trans=True)
+    assert relerr(Y, ref) <= TOL
+    C0 = rng.standard_normal((n_, nrhs))
+    Y = np.asfortranarray(C0.copy())
+    plan_interp.run_plan(P, X, Y, 0.3, 2.0, trans=True)
+    assert relerr(Y, 0.3 * ref + 2.0 * C0) <= TOL
+
+
 def test_subblock_is_rooted(hb, oracle):
     """matmul.jl:24: multiplying a sub-block ignores its own translators."""
     rng = np.random.default_rng(3)
