@@ -42,59 +42,72 @@ def env_int(name, default):
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
-         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-         "clocks_event_reasons.sw_power_cap")
+    """SM clock / power / throttle reasons DURING the timed region (B200_PROFILING.md).  Polls NVML
+    (nvidia_ml_py) every ~2 ms from a thread, because the timed region is only tens of
+    milliseconds long and `nvidia-smi -lms` cannot sample that fast; falls back to one
+    nvidia-smi query if NVML is unavailable."""
 
     def __init__(self, gpu_index):
-        self.proc, self.lines, self.idx = None, [], gpu_index
-        if shutil.which("nvidia-smi"):
-            try:
-                self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                              "-lms", "100", "-i", str(gpu_index)], stdout=subprocess.PIPE, text=True)
-                threading.Thread(target=self._pump, daemon=True).start()
-            except Exception:
-                self.proc = None
+        self.samples, self.stop_flag, self.thread, self.nv, self.h = [], False, None, None, None
+        self.idx = gpu_index
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[gpu_index]) if vis and all(t.strip().isdigit() for t in vis.split(",")) else gpu_index
+            self.nv, self.h = pynvml, pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.nv = None
 
-    def _pump(self):
-        for ln in self.proc.stdout:
-            self.lines.append((time.perf_counter(), ln.strip()))
+    def _poll(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                clk = nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)
+                try:
+                    reasons = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    reasons = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                pw = nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0
+                self.samples.append((time.perf_counter(), clk, reasons, pw))
+            except Exception:
+                pass
+            time.sleep(0.002)
 
     def stop(self, t0, t1):
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "nvidia-smi unavailable"}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, smax, reasons, power = [], None, set(), []
-        for t, ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                clk, mx = float(f[1]), float(f[2])
-            except ValueError:
-                continue
-            smax = mx
-            if t0 - 0.05 <= t <= t1 + 0.05:
-                sm.append(clk)
+        self.stop_flag = True
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        if not self.nv:
+            out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "note": "NVML unavailable"}
+            if shutil.which("nvidia-smi"):
                 try:
-                    power.append(float(f[3]))
-                except ValueError:
+                    q = subprocess.run(["nvidia-smi", "--query-gpu=clocks.sm,clocks.max.sm,clocks_event_reasons.active",
+                                        "--format=csv,noheader,nounits", "-i", str(self.idx)], capture_output=True, text=True, timeout=10)
+                    f = [x.strip() for x in q.stdout.strip().split(",")]
+                    out.update(sm_mhz=float(f[0]), sm_max_mhz=float(f[1]), note="single nvidia-smi sample after the timed region")
+                except Exception:
                     pass
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-        if not sm:  # region shorter than the sampling period: use every sample
-            for t, ln in self.lines:
-                f = [x.strip() for x in ln.split(",")]
-                try:
-                    sm.append(float(f[1]))
-                except (ValueError, IndexError):
-                    pass
-        sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": smax, "reasons": sorted(reasons),
-                "power_w_max": max(power) if power else None, "samples": len(sm)}
+            return out
+        nv = self.nv
+        inside = [s for s in self.samples if t0 <= s[0] <= t1]
+        window = "timed region"
+        if len(inside) < 3:  # very short region: widen to everything sampled under load (warm-up included)
+            inside, window = self.samples, "warm-up + timed region"
+        clks = sorted(s[1] for s in inside)
+        bits = 0
+        for s in inside:
+            bits |= s[2]
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+        return {"sm_mhz": clks[len(clks) // 2] if clks else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(k for k, v in names.items() if bits & v), "power_w_max": max((s[3] for s in inside), default=None),
+                "samples": len(inside), "window": window, "source": "NVML polled every 2 ms"}
 
 
 # ---------------------------------------------------------------------------
@@ -236,10 +249,10 @@ def main():
         P.matmul_dev(X.data_ptr(), rows, Y.data_ptr(), rows, k, 1.0, 0.0, stream=st)
 
     # ---------------- device-resident throughput (`value`) -------------------
+    sampler = ClockSampler(local) if rank == 0 else None
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = P.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     tw0 = time.perf_counter()

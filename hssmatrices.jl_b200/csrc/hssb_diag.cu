@@ -142,6 +142,37 @@ __global__ void __launch_bounds__(256, 1) dmma_loop_kernel(double* out, int iter
   if (s == 123.456) out[0] = s;
 }
 
+// Do DMMA (tensor path) and DFMA (FP64 pipe) share execution resources?  Even warps run the DMMA
+// loop, odd warps the DFMA loop; out[1..2] report nothing, the host derives the combined rate.
+__global__ void __launch_bounds__(256) mixed_fp64_kernel(double* out, int iters, double seed, int mode) {
+  const int warp = threadIdx.x >> 5;
+  const bool do_mma = mode == 0 ? true : mode == 1 ? false : (warp & 1) == 0;
+  double s = 0;
+  if (do_mma) {
+    double c[8][2];
+    const double a = seed + threadIdx.x * 1e-9, b = 1e-3 * seed;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) c[i][0] = c[i][1] = 0.0;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) mma_m8n8k4(c[i][0], c[i][1], a, b);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += c[i][0] + c[i][1];
+  } else {
+    double a[8], x = seed + threadIdx.x * 1e-9, y = 1.0 - 1e-9;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed * (i + 1);
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) a[i] = fma(a[i], y, x);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) s += a[i];
+  }
+  if (s == 123.456) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) copy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int64_t n) {
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
@@ -184,6 +215,24 @@ extern "C" int hssb_measure_peak(int device, int kind, int64_t arg, double* out)
       HSSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
       // DFMA: 8 FMAs/thread/iter; DMMA: 8 m8n8k4 (= 512 flops) per warp per iter
       const double flops = kind == 0 ? 2.0 * 8 * iters * 256.0 * grid : 8.0 * 512.0 * iters * 8.0 * grid;
+      if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    cudaFree(d);
+  } else if (kind == 7) {
+    // arg: 0 = all warps DMMA, 1 = all warps DFMA, 2 = half and half; returns combined TFLOP/s
+    const int mode = (int)arg, iters = 20000, grid = prop.multiProcessorCount * 4;
+    double* d = nullptr;
+    HSSB_CUDA(cudaMalloc(&d, 64));
+    for (int rep = 0; rep < 4; ++rep) {
+      HSSB_CUDA(cudaEventRecord(e0));
+      mixed_fp64_kernel<<<grid, 256>>>(d, iters, 0.5, mode);
+      HSSB_CUDA(cudaEventRecord(e1));
+      HSSB_CUDA(cudaEventSynchronize(e1));
+      float ms = 0;
+      HSSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      const double mma_warps = mode == 0 ? 8 : mode == 1 ? 0 : 4, fma_warps = 8 - mma_warps;
+      // per iteration: a DMMA warp does 8 x 512 flops, a DFMA warp 8 x 64 flops
+      const double flops = (mma_warps * 8 * 512.0 + fma_warps * 8 * 64.0) * iters * (double)grid;
       if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
     }
     cudaFree(d);
