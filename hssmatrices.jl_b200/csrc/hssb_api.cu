@@ -1215,8 +1215,9 @@ static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t r
   const int64_t sx = std::max<int64_t>(rows_x, 1), sy = rows_y;
   // The product is independent per right-hand side, so the call is pipelined over column blocks:
   // H2D of block j+1 (copy-in stream), the product of block j (compute stream) and D2H of block
-  // j-1 (copy-out stream) overlap; PCIe is full duplex.  Blocks are a multiple of the widest
-  // kernel tile that still leaves >= 2 blocks, so the tiles stay full.
+  // j-1 (copy-out stream) overlap; PCIe is full duplex.  The transfers dominate (2*n*nrhs*8 bytes
+  // over PCIe against ~1 ms of kernels), so the blocks are small (about nrhs/8 columns) even
+  // though narrow blocks leave the kernels' column tiles partly empty.
   if (!h->copy_in) {
     HSSB_CUDA(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
     HSSB_CUDA(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
@@ -1227,7 +1228,7 @@ static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t r
   }
   int64_t cb = nrhs;
   if (h->pipeline_cols > 0) cb = std::min<int64_t>(nrhs, h->pipeline_cols);
-  else if (nrhs >= 32 && (int64_t)(rows_x + rows_y) * nrhs * 8 >= ((int64_t)64 << 20)) cb = std::max<int64_t>(16, (nrhs + 3) / 4 / 16 * 16);
+  else if (nrhs >= 16 && (int64_t)(rows_x + rows_y) * nrhs * 8 >= ((int64_t)64 << 20)) cb = std::max<int64_t>(8, ((nrhs + 7) / 8 + 7) / 8 * 8);  // ~8 blocks: measured best on PCIe Gen5 (tools/e2e_blocks.py)
   int64_t nblk = (nrhs + cb - 1) / cb;
   if (nblk > hssb_matrix::MAX_BLOCKS) { cb = (nrhs + hssb_matrix::MAX_BLOCKS - 1) / hssb_matrix::MAX_BLOCKS; nblk = (nrhs + cb - 1) / cb; }
   // copies of this call must not overtake the previous call's use of the staging buffers
