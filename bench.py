@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", default="default", help="kernel variant switches, e.g. generic, nograph, fused")
+    ap.add_argument("--variant", default="default", help="kernel variant switches: generic, nograph, nccl")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = dict(CONFIGS[args.config])
@@ -225,8 +225,6 @@ def main():
         exchange = "nccl all-gather"
     if "generic" in variants:
         P.set_option(hb.OPT_FORCE_GENERIC, 1)
-    if "fused" in variants:
-        P.set_option(hb.OPT_FUSED_LEAF, 1)
     P.set_option(hb.OPT_USE_GRAPH, 0 if "nograph" in variants else 1)
     rows = P.info.local_n
     # a dedicated non-default stream: the library launches on it and torch's events time it

@@ -24,7 +24,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libhssb200.so")
 __all__ = [
     "HssMatrix", "PackedHss", "DimensionMismatch", "HssbError", "bisection_cluster", "ClusterTree",
     "isleaf", "isbranch", "size", "gensize", "rooted", "checkdims", "pack", "mul_", "synthetic",
-    "lib", "device_count", "measure_peak",
+    "lib", "device_count", "measure_peak", "load",
 ]
 
 
@@ -85,6 +85,8 @@ SIGNATURES = {
     "hssb_builder_finalize": (C.c_int, [_P, _i64, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "hssb_create_synthetic": (C.c_int, [_i64, _i64, _i64, C.c_uint64, C.c_int, C.c_int, C.c_int, C.POINTER(_P)]),
     "hssb_synthetic_rhs": (C.c_int, [C.c_uint64, _i64, _i64, _i64, _i64, _P, _i64, C.c_int, _P]),
+    "hssb_save": (C.c_int, [_P, C.c_char_p]),
+    "hssb_load": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_P)]),
     "hssb_destroy": (C.c_int, [_P]),
     "hssb_info": (C.c_int, [_P, C.POINTER(_Info)]),
     "hssb_node_info": (C.c_int, [_P, _i64, C.POINTER(_NodeT)]),
@@ -113,7 +115,7 @@ SIGNATURES = {
     "hssb_debug_pool": (C.c_int, [_P, _P, _i64]),
 }
 
-OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_FUSED_LEAF, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS = 1, 2, 3, 4, 5, 6
+OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS = 1, 2, 4, 5, 6
 PHASE_NAMES = ("leaf_up", "merge", "exchange", "translate", "leaf_down", "exchange_ack")
 KIND_NAMES = ("D", "U", "V", "B12", "B21", "R", "W")
 
@@ -414,6 +416,13 @@ def synthetic(n, leafsize, rank, seed, device=0, shard_rank=0, n_shards=1, plan_
     return PackedHss(h)
 
 
+def load(path, device=0):
+    """Load a packed matrix written by PackedHss.save(); device=-1 gives a host-only handle."""
+    h = C.c_void_p()
+    _check(lib().hssb_load(os.fsencode(path), device, C.byref(h)))
+    return PackedHss(h)
+
+
 class PackedHss:
     """Handle to a packed, device-resident HSS matrix (hssb_matrix*)."""
 
@@ -442,6 +451,10 @@ class PackedHss:
     def __exit__(self, *a):
         self.close()
 
+    def save(self, path):
+        """Write the packed format (tree shape + level-ordered pool) to `path`."""
+        _check(lib().hssb_save(self._h, os.fsencode(path)))
+
     # queries ---------------------------------------------------------------
     @property
     def shape(self):
@@ -462,16 +475,18 @@ class PackedHss:
             kind = KIND_NAMES.index(kind)
         nd = self.node(node)
         par = self.node(nd.parent) if nd.parent >= 0 else None
+        leaf = bool(nd.is_leaf) and not nd.is_remote
+        branch = not nd.is_leaf and not nd.is_remote
         if kind == 0:
-            shp = (nd.m, nd.n)
+            shp = (nd.m, nd.n) if leaf else (0, 0)
         elif kind == 1:
-            shp = (nd.m, nd.kr)
+            shp = (nd.m, nd.kr) if leaf else (0, 0)
         elif kind == 2:
-            shp = (nd.n, nd.kw)
+            shp = (nd.n, nd.kw) if leaf else (0, 0)
         elif kind == 3:
-            shp = (self.node(nd.left).kr, self.node(nd.right).kw)
+            shp = (self.node(nd.left).kr, self.node(nd.right).kw) if branch else (0, 0)
         elif kind == 4:
-            shp = (self.node(nd.right).kr, self.node(nd.left).kw)
+            shp = (self.node(nd.right).kr, self.node(nd.left).kw) if branch else (0, 0)
         elif kind == 5:
             shp = (nd.kr, par.kr if par else 0)
         else:

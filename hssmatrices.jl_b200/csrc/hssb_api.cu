@@ -501,7 +501,7 @@ static int plan_matrix(hssb_matrix* H) {
 }
 
 // Device part: allocate the pool, upload (or generate) the generators and the task table.
-static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src) {
+static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src, FILE* pool_file = nullptr) {
   int rc = plan_matrix(H);
   if (rc) return rc;
   auto& nodes = H->nodes;
@@ -518,7 +518,22 @@ static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src) {
     HSSB_CUDA(cudaMemcpyAsync(H->tasks_dev, H->tasks_host.data(), H->tasks_host.size() * sizeof(GTask),
                               cudaMemcpyHostToDevice, H->stream));
   }
-  if (src) {
+  if (pool_file) {
+    // packed pool image from a file written by hssb_save: stream it through a pinned buffer
+    const size_t CH = (size_t)1 << 22;
+    double* stage = nullptr;
+    HSSB_CUDA(cudaMallocHost(&stage, CH * sizeof(double)));
+    for (int64_t off = 0; off < H->pool_len; off += (int64_t)CH) {
+      const size_t cnt = (size_t)std::min<int64_t>((int64_t)CH, H->pool_len - off);
+      if (fread(stage, sizeof(double), cnt, pool_file) != cnt) {
+        cudaFreeHost(stage);
+        HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: file is truncated");
+      }
+      HSSB_CUDA(cudaMemcpyAsync(H->pool_dev + off, stage, cnt * sizeof(double), cudaMemcpyHostToDevice, H->stream));
+      HSSB_CUDA(cudaStreamSynchronize(H->stream));
+    }
+    cudaFreeHost(stage);
+  } else if (src) {
     // host generators: assemble in pinned chunks and upload
     const size_t CH = (size_t)1 << 22;  // 32 MiB of doubles per chunk
     double* stage[2] = {nullptr, nullptr};
@@ -1294,7 +1309,6 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
   switch (opt) {
     case HSSB_OPT_FORCE_GENERIC: h->force_generic = value != 0; break;
     case HSSB_OPT_USE_GRAPH: h->use_graph = value != 0; break;
-    case HSSB_OPT_FUSED_LEAF: h->fused_leaf = value != 0; break;
     case HSSB_OPT_PROFILE: h->profile = value != 0; break;
     case HSSB_OPT_DEBUG: h->debug_mode = (int)value; break;
     case HSSB_OPT_PIPELINE_COLS: h->pipeline_cols = value; break;
@@ -1311,7 +1325,6 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
   switch (opt) {
     case HSSB_OPT_FORCE_GENERIC: return h->force_generic;
     case HSSB_OPT_USE_GRAPH: return h->use_graph;
-    case HSSB_OPT_FUSED_LEAF: return h->fused_leaf;
     case HSSB_OPT_PROFILE: return h->profile;
     default: return -1;
   }
@@ -1409,6 +1422,106 @@ int hssb_xchg_import(hssb_matrix* h, const void* all_handles, int n_ranks) {
   }
   h->peer_xchg = true;
   invalidate_graphs(h);
+  return HSSB_OK;
+}
+
+// ---- packed format on disk -------------------------------
+// The reference has no serialisation; the packed format (tree shape + level-ordered pool) is the
+// natural file format: fixtures become reproducible without Julia, and a packed matrix can be
+// checkpointed / reloaded without re-walking the pointer tree.
+struct FileHeader {
+  char magic[8];
+  uint32_t version, node_words;
+  int64_t n_nodes, pool_len;
+  int32_t shard_rank, n_shards, synthetic, padded;
+  uint64_t seed;
+  int64_t synth_rank;
+};
+static const char kMagic[8] = {'H', 'S', 'S', 'B', '2', '0', '0', 0};
+static const uint32_t kFileVersion = 2;  // bump whenever layout_pool / stored_transposed change
+static const uint32_t kNodeWords = 9;
+
+int hssb_save(const hssb_matrix* h, const char* path) {
+  if (!h || !path) HSSB_FAIL(HSSB_ERR_ARG, "hssb_save: NULL argument");
+  FILE* fp = fopen(path, "wb");
+  if (!fp) HSSB_FAIL(HSSB_ERR_ARG, "hssb_save: cannot open %s for writing", path);
+  FileHeader hd;
+  memset(&hd, 0, sizeof(hd));
+  memcpy(hd.magic, kMagic, 8);
+  hd.version = kFileVersion; hd.node_words = kNodeWords;
+  hd.n_nodes = (int64_t)h->nodes.size(); hd.pool_len = h->pool_len;
+  hd.shard_rank = h->shard_rank; hd.n_shards = h->n_shards; hd.synthetic = h->synthetic; hd.padded = h->padded;
+  hd.seed = h->seed; hd.synth_rank = h->synth_rank;
+  bool ok = fwrite(&hd, sizeof(hd), 1, fp) == 1;
+  for (const Node& t : h->nodes) {
+    const int64_t w[kNodeWords] = {t.left, t.right, t.leaf, t.remote, t.m, t.n, t.kr, t.kw, (int64_t)t.heap_id};
+    ok = ok && fwrite(w, sizeof(int64_t), kNodeWords, fp) == kNodeWords;
+  }
+  if (ok && h->device < 0) {
+    ok = fwrite(h->pool_host.data(), sizeof(double), (size_t)h->pool_len, fp) == (size_t)h->pool_len;
+  } else if (ok) {
+    DeviceGuard dg(h->device);
+    const size_t CH = (size_t)1 << 22;
+    std::vector<double> buf(CH);
+    for (int64_t off = 0; ok && off < h->pool_len; off += (int64_t)CH) {
+      const size_t cnt = (size_t)std::min<int64_t>((int64_t)CH, h->pool_len - off);
+      if (cudaMemcpy(buf.data(), h->pool_dev + off, cnt * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+      ok = fwrite(buf.data(), sizeof(double), cnt, fp) == cnt;
+    }
+  }
+  ok = (fclose(fp) == 0) && ok;
+  if (!ok) HSSB_FAIL(HSSB_ERR_ARG, "hssb_save: write to %s failed", path);
+  return HSSB_OK;
+}
+
+// device >= 0: load onto that GPU; device < 0: host-only (plan-only) handle for CPU-side inspection.
+int hssb_load(const char* path, int device, hssb_matrix** out) {
+  if (!path || !out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: NULL argument");
+  *out = nullptr;
+  if (device >= 0) { int rc = check_device(device); if (rc) return rc; }
+  FILE* fp = fopen(path, "rb");
+  if (!fp) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: cannot open %s", path);
+  struct Closer { FILE* f; ~Closer() { if (f) fclose(f); } } closer{fp};
+  FileHeader hd;
+  if (fread(&hd, sizeof(hd), 1, fp) != 1 || memcmp(hd.magic, kMagic, 8) != 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: %s is not an hssb200 file", path);
+  if (hd.version != kFileVersion || hd.node_words != kNodeWords) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: file version %u, library reads %u", hd.version, kFileVersion);
+  if (hd.n_nodes <= 0 || hd.pool_len <= 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: corrupt header");
+  std::unique_ptr<hssb_matrix> H(new (std::nothrow) hssb_matrix());
+  if (!H) HSSB_FAIL(HSSB_ERR_ALLOC, "hssb_load: out of memory");
+  H->device = device < 0 ? -1 : device;
+  H->shard_rank = hd.shard_rank; H->n_shards = hd.n_shards;
+  H->synthetic = hd.synthetic != 0; H->seed = hd.seed; H->synth_rank = hd.synth_rank;
+  H->nodes.resize((size_t)hd.n_nodes);
+  for (Node& t : H->nodes) {
+    int64_t w[kNodeWords];
+    if (fread(w, sizeof(int64_t), kNodeWords, fp) != kNodeWords) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: file is truncated");
+    t.left = w[0]; t.right = w[1]; t.leaf = w[2] != 0; t.remote = w[3] != 0;
+    t.m = w[4]; t.n = w[5]; t.kr = w[6]; t.kw = w[7]; t.heap_id = (uint64_t)w[8];
+    if ((!t.leaf && !t.remote) && (t.left <= 0 || t.right <= 0 || t.left >= hd.n_nodes || t.right >= hd.n_nodes))
+      HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: corrupt node table");
+  }
+  int rc;
+  if (device < 0) {
+    rc = plan_matrix(H.get());
+    if (!rc && H->pool_len != hd.pool_len) { set_error("hssb_load: pool layout mismatch"); rc = HSSB_ERR_ARG; }
+    if (!rc) {
+      H->pool_host.resize((size_t)H->pool_len);
+      if (fread(H->pool_host.data(), sizeof(double), (size_t)H->pool_len, fp) != (size_t)H->pool_len) { set_error("hssb_load: file is truncated"); rc = HSSB_ERR_ARG; }
+    }
+    if (rc) return rc;
+  } else {
+    // plan first (host), so that a layout mismatch is caught before anything is uploaded
+    {
+      hssb_matrix probe;
+      probe.device = -1; probe.shard_rank = H->shard_rank; probe.n_shards = H->n_shards; probe.nodes = H->nodes;
+      rc = plan_matrix(&probe);
+      if (rc) return rc;
+      if (probe.pool_len != hd.pool_len) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: pool layout mismatch (file %lld, library %lld doubles)", (long long)hd.pool_len, (long long)probe.pool_len);
+    }
+    rc = finish_matrix(H.get(), nullptr, fp);
+    if (rc) { hssb_destroy(H.release()); return rc; }
+  }
+  *out = H.release();
   return HSSB_OK;
 }
 

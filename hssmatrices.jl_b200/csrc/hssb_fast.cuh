@@ -5,11 +5,11 @@
 // mma.sync m8n8k4 (DMMA.8x8x4 in SASS).  All operands are staged in shared
 // memory with a leading dimension == 4 (mod 16) doubles, which makes every
 // fragment load of hssb_mma.cuh bank-conflict free:
-//   "N" operand  A(i,k) at s[k*ld + i]   (D, U, B12, B21, R)        lane -> s[(k0+t)*ld + i0+g]
-//   "T" operand  A(i,k) at s[i*ld + k]   (V', W', and every B(k,j) = s[j*ld + k])
-// Global -> shared copies are 16-byte cp.async (LDGSTS), column by column, so
-// arbitrary pool offsets work as long as columns are 16-byte aligned (the
-// packer guarantees it).
+//   A operands  A(i,k) at s[k*ld + i]   (D, U, V', W', B12, B21, R)   lane -> s[(k0+t)*ld + i0+g]
+//   B operands  B(k,j) at s[j*ld + k]   (Z, F tiles)                  lane -> s[(j0+g)*ld + k0+t]
+// The pool and the workspaces already carry that padding, so global -> shared is ONE
+// cp.async.bulk (UBLKCP) per block; the caller's X comes in through a tiled 2-D TMA tensor map
+// with 128-byte swizzle (UTMALDG).  Completion is tracked in bytes on mbarriers.
 //
 // Kernels
 //   stream_leaf_kernel<M,R,false>  Z = V' X               persistent, warp-specialised (TMA producer warp)
@@ -26,28 +26,6 @@
 namespace hssb {
 
 enum FastKind : int { FAST_NONE = 0, FAST_LEAF_UP = 1, FAST_MERGE = 2, FAST_TRANSLATE = 3, FAST_LEAF_DOWN = 4 };
-
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
-  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
-}
-
-// Copies a rows x cols column-major block (rows even, columns 16-byte aligned)
-// from global (leading dimension lds) to shared (leading dimension ldd).
-template <int THREADS>
-__device__ __forceinline__ void copy_block_async(double* dst, int ldd, const double* src, int64_t lds, int rows, int cols,
-                                                 int tid) {
-  const int h = rows >> 1;  // 16-byte chunks per column
-  for (int idx = tid; idx < h * cols; idx += THREADS) {
-    const int c = idx / h, r2 = (idx - c * h) << 1;
-    cp_async16(dst + c * ldd + r2, src + (int64_t)c * lds + r2);
-  }
-}
 
 // ------------------------------------------------- TMA bulk copy + mbarrier ---
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }

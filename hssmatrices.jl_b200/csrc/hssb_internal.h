@@ -148,7 +148,7 @@ struct hssb_matrix {
   unsigned long long* peer_flags[MAX_PEERS] = {};  // [0,P): data flags, [P,2P): ack flags, [2P]: epoch, [2P+1]: ticket
   unsigned long long* my_flags = nullptr;
   // options
-  bool force_generic = false, use_graph = false, fused_leaf = false, profile = false;
+  bool force_generic = false, use_graph = false, profile = false;
   int debug_mode = 0;
   bool in_host_call = false;
   std::vector<cudaEvent_t> prof_events;  // HSSB_OPT_PROFILE: one event between consecutive phases

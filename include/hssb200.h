@@ -100,6 +100,12 @@ int hssb_create_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t se
 int hssb_synthetic_rhs(uint64_t seed, int64_t n, int64_t nrhs, int64_t row0, int64_t rows,
                        double* dX, int64_t ldx, int device, void* stream);
 
+/* The packed format as a file (checkpoint / fixture exchange; the reference has no serialisation):
+ * tree shape + level-ordered pool, versioned.  hssb_load with device < 0 gives a host-only handle
+ * (inspection, hssb_get_block), with device >= 0 a ready-to-multiply device-resident matrix.       */
+int hssb_save(const hssb_matrix* h, const char* path);
+int hssb_load(const char* path, int device, hssb_matrix** out);
+
 int hssb_destroy(hssb_matrix* h);
 
 /* ---- queries ---------------------------------------------------------- */
@@ -163,7 +169,6 @@ int hssb_sync(hssb_matrix* h);
 /* Options. */
 #define HSSB_OPT_FORCE_GENERIC 1 /* 1: never use the fixed-shape DMMA kernels (debug/parity)  */
 #define HSSB_OPT_USE_GRAPH 2     /* 1: replay the level schedule as a CUDA graph              */
-#define HSSB_OPT_FUSED_LEAF 3    /* 1: form D*X in the upsweep leaf kernel (north-star variant) */
 #define HSSB_OPT_PROFILE 4       /* 1: record a CUDA event between phases (hssb_phase_time)   */
 #define HSSB_OPT_DEBUG 5         /* measurement only, WRONG RESULTS: bit 0 = leaf kernels compute on whatever is in
                                     shared memory without waiting for data, bit 1 = move data without computing */

@@ -102,6 +102,20 @@ def test_transposed_product(gpu, oracle):
         assert relerr(Ps @ Xs, oracle.matmul(hs, Xs)) <= TOL
 
 
+def test_save_load_device(gpu, oracle, tmp_path):
+    """hssb_save from the device, hssb_load back onto the device: identical products."""
+    n, ls, r, k, seed = 2048, 128, 32, 16, 21
+    X = oracle.synth_x(seed, n, k)
+    f = str(tmp_path / "synth.hssb")
+    with gpu.synthetic(n, ls, r, seed) as P:
+        Y = P @ X
+        P.save(f)
+    with gpu.load(f) as Q:
+        assert Q.info.uniform == 1
+        assert np.array_equal(Q @ X, Y)
+    assert relerr(Y, oracle.matmul(oracle.synthetic_hss(n, ls, r, seed), X)) <= TOL
+
+
 def test_golden_fixtures(gpu, oracle):
     import make_golden
     gdir = os.path.join(os.path.dirname(__file__), "golden")

@@ -191,6 +191,31 @@ def test_sharded_from_host_tree(hb, oracle):
     assert relerr(np.vstack(Ys), ref) <= TOL
 
 
+def test_save_load_roundtrip(hb, oracle, tmp_path):
+    """Packed format as a file: same blocks, same plan after a round trip."""
+    rng = np.random.default_rng(31)
+    cl = oracle.bisection_cluster(300, 40)
+    h = oracle.random_hss(cl, cl, rng, 0, 6)
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    f = str(tmp_path / "m.hssb")
+    P.save(f)
+    Q = hb.load(f, device=-1)
+    assert Q.shape == P.shape and Q.info.n_nodes == P.info.n_nodes and Q.info.flops_per_rhs == P.info.flops_per_rhs
+    for node in range(P.info.n_nodes):
+        for kind in range(7):
+            assert np.array_equal(P.block(node, kind), Q.block(node, kind))
+    X = rng.standard_normal((300, 3))
+    Y = np.zeros((300, 3), order="F")
+    plan_interp.run_plan(Q, X, Y)
+    assert relerr(Y, oracle.matmul(h, X)) <= TOL
+    with open(f, "r+b") as fh:      # a damaged file must be rejected, not half-loaded
+        fh.truncate(200)
+    with pytest.raises(hb.HssbError):
+        hb.load(f, device=-1)
+    with pytest.raises(hb.HssbError):
+        hb.load(str(tmp_path / "missing.hssb"), device=-1)
+
+
 def test_dimension_mismatch(hb, oracle):
     rng = np.random.default_rng(1)
     cl = oracle.bisection_cluster(64, 16)
