@@ -65,7 +65,13 @@ __global__ void __launch_bounds__(256, 1) dmma_loop_kernel(double* out, int iter
   constexpr int LDA = 132, LDX = 132, KC = 64;
   double* As = sm;              // [KC][LDA]
   double* Xs = sm + KC * LDA;   // [64][LDX]
-  for (int i = threadIdx.x; i < KC * LDA + 64 * LDX; i += blockDim.x) sm[i] = 1e-3 * (i % 7);
+  // iters < 0: random operands (does the FP64 tensor rate depend on the data / power?)
+  for (int i = threadIdx.x; i < KC * LDA + 64 * LDX; i += blockDim.x) {
+    unsigned long long h = (i + 1) * 0x9E3779B97F4A7C15ull + blockIdx.x * 0xBF58476D1CE4E5B9ull;
+    h ^= h >> 31; h *= 0x94D049BB133111EBull; h ^= h >> 29;
+    sm[i] = iters < 0 ? ((double)(long long)(h >> 11) * (1.0 / 9007199254740992.0) - 0.5) * 1e-2 : 1e-3 * (i % 7);
+  }
+  if (iters < 0) iters = -iters;
   __syncthreads();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
   const int wm = warp % 4, wn = warp / 4;
@@ -256,8 +262,8 @@ extern "C" int hssb_measure_peak(int device, int kind, int64_t arg, double* out)
     cudaFree(d);
   } else if (kind == 4 || kind == 5 || kind == 6) {
     // arg = CTAs per SM (1 or 2)
-    const int per_sm = arg >= 1 && arg <= 2 ? (int)arg : 1;
-    const int iters = 400, grid = prop.multiProcessorCount * per_sm;
+    const int per_sm = 1;
+    const int iters = arg < 0 ? -2000 : 2000, grid = prop.multiProcessorCount * per_sm;  // arg < 0: random operands
     const size_t smem = sizeof(double) * (64 * 132 + 64 * 132);
     double* d = nullptr;
     HSSB_CUDA(cudaMalloc(&d, 64));
@@ -273,7 +279,7 @@ extern "C" int hssb_measure_peak(int device, int kind, int64_t arg, double* out)
       HSSB_CUDA(cudaEventSynchronize(e1));
       float ms = 0;
       HSSB_CUDA(cudaEventElapsedTime(&ms, e0, e1));
-      const double flops = 2.0 * 128 * 64 * 64 * (double)iters * grid;  // 128x64 tile, K = 64 per iteration
+      const double flops = 2.0 * 128 * 64 * 64 * (double)(iters < 0 ? -iters : iters) * grid;  // 128x64 tile, K = 64 per iteration
       if (rep > 0) best = std::max(best, flops / (ms * 1e-3) * 1e-12);
     }
     cudaFree(d);

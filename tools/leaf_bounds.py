@@ -8,7 +8,7 @@ P = hb.synthetic(n, ls, r, seed)
 s = torch.cuda.Stream(); torch.cuda.set_stream(s)
 X = torch.randn((k, n), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
 P.set_option(hb.OPT_USE_GRAPH, 0); P.set_option(hb.OPT_PROFILE, 1)
-for mode, name in ((0, "normal (staggered)"), (8, "normal, no stagger"), (1, "compute-only"), (9, "compute-only, no stagger"), (2, "move-only")):
+for mode, name in ((0, "normal"), (1, "compute-only (no data waits)"), (5, "compute-only, no stores"), (2, "move-only (no DMMA)")):
     P.set_option(hb.OPT_DEBUG, mode)
     acc = {}
     for it in range(6):
