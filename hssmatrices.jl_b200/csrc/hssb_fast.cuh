@@ -84,6 +84,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 // Warp 8 is the producer: it issues one cp.async.bulk per column (so the shared-memory image can
 // carry the conflict-free +4 padding) and tracks completion in bytes on mbarriers.  Warps 0-7
 // only wait, load fragments and issue DMMAs; they hand buffers back through "empty" mbarriers.
+#ifndef HSSB_ENABLE_DEBUG_MODES
+#define HSSB_ENABLE_DEBUG_MODES 0
+#endif
 #ifndef HSSB_DOWN_WARPS
 #define HSSB_DOWN_WARPS 8
 #endif
@@ -155,7 +158,11 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
 
   auto item_cols = [&](int item) { return min(C::NT, nrhs - ((first + item) % ntiles) * C::NT); };
 
+#if HSSB_ENABLE_DEBUG_MODES  // measurement builds only (make DEBUG_MODES=1): tools/leaf_bounds.py
   const bool dbg_nowait = p.debug & 1, dbg_nomma = p.debug & 2, dbg_nostore = p.debug & 4;
+#else
+  constexpr bool dbg_nowait = false, dbg_nomma = false, dbg_nostore = false;
+#endif
   if (warp == C::NWARPS) {
     if (dbg_nowait) return;
     // ====================== producer warp ======================

@@ -170,7 +170,7 @@ int hssb_sync(hssb_matrix* h);
 #define HSSB_OPT_FORCE_GENERIC 1 /* 1: never use the fixed-shape DMMA kernels (debug/parity)  */
 #define HSSB_OPT_USE_GRAPH 2     /* 1: replay the level schedule as a CUDA graph              */
 #define HSSB_OPT_PROFILE 4       /* 1: record a CUDA event between phases (hssb_phase_time)   */
-#define HSSB_OPT_DEBUG 5         /* measurement only, WRONG RESULTS: bit 0 = leaf kernels compute on whatever is in
+#define HSSB_OPT_DEBUG 5         /* measurement only (library built with make DEBUG_MODES=1), WRONG RESULTS: bit 0 = leaf kernels compute on whatever is in
                                     shared memory without waiting for data, bit 1 = move data without computing */
 #define HSSB_OPT_PIPELINE_COLS 6 /* host entry: right-hand sides per pipelined block (0 = automatic)  */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
