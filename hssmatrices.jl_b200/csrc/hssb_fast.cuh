@@ -15,6 +15,7 @@
 //   stream_leaf_kernel<M,R,false>  Z = V' X               persistent, warp-specialised (TMA producer warp)
 //   stream_leaf_kernel<M,R,true>   Y = a (D X + U F) + b Y   same kernel, [D U] streamed by K chunks
 //   stream_node_kernel<R>          Z = W1' Z1 + W2' Z2  and  F1 = B12 Z2 + R1 F   persistent, warp-specialised
+//   oneshot_node_kernel<R>         same, one CTA per item (small ranks, single column tile)
 #pragma once
 
 #include <cuda.h>
@@ -508,6 +509,82 @@ stream_node_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
   }
 }
 
+// One-shot flavour of the node kernel: one CTA of 128 threads per (task, 64-column tile), four
+// bulk copies on one mbarrier, no pipeline inside the CTA; latency is hidden by running four such
+// CTAs per SM.  Slightly faster than the persistent kernel for small ranks and a single column
+// tile (config 3), where an item is only ~0.5 us of DMMA work.
+template <int R>
+struct OneShotCfg {
+  static constexpr int NT = 64, LD = R + 4, TN = 2;
+  static constexpr size_t SMEM = 128 + sizeof(double) * (2 * R * LD + 2 * NT * LD);
+};
+
+template <int R>
+__global__ void __launch_bounds__(128)
+oneshot_node_kernel(const GTask* __restrict__ tasks, CallParams p) {
+  using C = OneShotCfg<R>;
+  extern __shared__ __align__(1024) unsigned char smem_raw[];
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
+  double* As = reinterpret_cast<double*>(smem_raw + 128);  // [2][R][LD]   A(i,k) at [k*LD + i]
+  double* Bs = As + 2 * R * C::LD;                         // [2][NT][LD]  B(k,j) at [j*LD + k]
+  const GTask tk = tasks[blockIdx.x];
+  const int tile = blockIdx.y, nrhs = p.nrhs;
+  const int ncols = min(C::NT, nrhs - tile * C::NT);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const bool two = tk.K1 > 0;
+  const int64_t toff = (int64_t)tile * C::NT * C::LD;
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+    constexpr uint32_t ab = R * C::LD * 8;
+    const uint32_t bb = (uint32_t)(ncols * C::LD * 8);
+    mbar_expect_tx(bar, two ? 2 * (ab + bb) : ab + bb);
+    bulk_g2s(As, p.pool + tk.a0, ab, bar);
+    bulk_g2s(Bs, (tk.sb0 == SRC_F ? p.F : p.Z) + tk.b0 * (int64_t)nrhs + toff, bb, bar);
+    if (two) {
+      bulk_g2s(As + R * C::LD, p.pool + tk.a1, ab, bar);
+      bulk_g2s(Bs + C::NT * C::LD, (tk.sb1 == SRC_F ? p.F : p.Z) + tk.b1 * (int64_t)nrhs + toff, bb, bar);
+    }
+  }
+  __syncthreads();  // the barrier is initialised before anyone polls it
+  mbar_wait(bar, 0);
+
+  double acc[R / 8][C::TN][2];
+#pragma unroll
+  for (int i = 0; i < R / 8; ++i)
+#pragma unroll
+    for (int j = 0; j < C::TN; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+  const int col0 = warp * 16;
+  const int nsrc = two ? 2 : 1;
+  for (int s = 0; s < nsrc; ++s) {
+    const double* A = As + s * R * C::LD + g + t * C::LD;
+    const double* B = Bs + s * C::NT * C::LD + (col0 + g) * C::LD + t;
+#pragma unroll
+    for (int kk = 0; kk < R / 4; ++kk) {
+      double b[C::TN];
+#pragma unroll
+      for (int j = 0; j < C::TN; ++j) b[j] = B[j * 8 * C::LD + kk * 4];
+#pragma unroll
+      for (int i = 0; i < R / 8; ++i) {
+        const double a = A[kk * 4 * C::LD + i * 8];
+#pragma unroll
+        for (int j = 0; j < C::TN; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a, b[j]);
+      }
+    }
+  }
+  double* O = (tk.sc == SRC_F ? p.F : p.Z) + tk.c * (int64_t)nrhs + toff;
+#pragma unroll
+  for (int j = 0; j < C::TN; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = col0 + j * 8 + 2 * t + e;
+      if (col < ncols) {
+#pragma unroll
+        for (int i = 0; i < R / 8; ++i) O[(int64_t)col * C::LD + i * 8 + g] = acc[i][j][e];
+      }
+    }
+}
+
 // ================================================================ host side ===
 struct FastState {
   int num_sms = 148;
@@ -585,6 +662,17 @@ static int launch_node_nt(hssb_matrix* H, const Phase& ph, const CallParams& cp,
 
 template <int R>
 static int launch_node(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
+  if constexpr (R <= 32) {
+    if (cp.nrhs > 32 && cp.nrhs <= 64) {  // one full-width tile of little work per item: one-shot CTAs, 4 per SM
+      using C = OneShotCfg<R>;
+      FastState* fs = (FastState*)H->fast_state;
+      if (int rc = fs->configure((const void*)oneshot_node_kernel<R>, C::SMEM)) return rc;
+      oneshot_node_kernel<R><<<dim3((unsigned)ph.ntasks, 1), 128, C::SMEM, st>>>(H->tasks_dev + ph.task0, cp);
+      H->launches++;
+      HSSB_CUDA(cudaGetLastError());
+      return HSSB_OK;
+    }
+  }
   // the last (or only) column tile is at most half full with 64-wide tiles: use 32-wide ones
   const int rem = cp.nrhs % 64;
   if (rem > 0 && rem <= 32 && cp.nrhs < 128) return launch_node_nt<R, 32>(H, ph, cp, st);
