@@ -119,6 +119,21 @@ end
 *(p::PackedHss, B::StridedMatrix{Float64}) = mul!(Matrix{Float64}(undef, size(p, 1), size(B, 2)), p, B, 1.0, 0.0)   # src/matmul.jl:13
 *(p::PackedHss, x::StridedVector{Float64}) = reshape(p * reshape(x, length(x), 1), length(x))                      # src/matmul.jl:15
 
+# A * hssB (src/matmul.jl:14) without the adjoint copy of src/hssmatrix.jl:165-171:
+# A*hssB = (hssB' * A')', and hssB' * X is hssb_matmul_t on the same packed generators.
+function tmul!(C::StridedMatrix{Float64}, p::PackedHss, B::StridedMatrix{Float64}, α::Real, β::Real)
+  size(p, 1) == size(B, 1) || throw(DimensionMismatch("First dimension of B does not match first dimension of A."))
+  size(C) == (size(p, 2), size(B, 2)) || throw(DimensionMismatch("Dimensions of C don't match up with A' and B."))
+  GC.@preserve B C begin
+    check(ccall((:hssb_matmul_t, libhssb), Cint,
+      (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Float64),
+      p.handle, size(C, 1), size(B, 1), size(B, 2), pointer(B), max(stride(B, 2), 1), pointer(C), max(stride(C, 2), 1),
+      Float64(α), Float64(β)))
+  end
+  return C
+end
+*(A::StridedMatrix{Float64}, p::PackedHss) = copy(tmul!(Matrix{Float64}(undef, size(p, 2), size(A, 1)), p, copy(A'), 1.0, 0.0)')
+
 # ---- drop-in methods on HssMatrix{Float64} ---------------------------------------------------
 # HssMatrix is mutable (recompress!, prune_leaves!, field assignment as in test/runtests.jl:75), so
 # the device copy is cached per object identity and must be dropped by hand after a mutation.
@@ -129,6 +144,7 @@ invalidate!(hssA::HssMatrix{Float64}) = (delete!(CACHE, hssA); nothing)
 
 mul!(C::StridedMatrix{Float64}, hssA::HssMatrix{Float64}, B::StridedMatrix{Float64}, α::Real, β::Real) = mul!(C, packed(hssA), B, α, β)
 *(hssA::HssMatrix{Float64}, B::StridedMatrix{Float64}) = packed(hssA) * B
+*(A::StridedMatrix{Float64}, hssB::HssMatrix{Float64}) = A * packed(hssB)
 
 export pack, PackedHss, invalidate!
 
