@@ -116,6 +116,25 @@ def test_save_load_device(gpu, oracle, tmp_path):
     assert relerr(Y, oracle.matmul(oracle.synthetic_hss(n, ls, r, seed), X)) <= TOL
 
 
+def test_fuzz_arbitrary_trees(gpu, oracle):
+    """Random unbalanced trees (rectangular leaves, ranks 0..4, leaves at different depths) through
+    the host entry, forward and transposed, against the dense expansion."""
+    from test_plan_property import random_tree
+    for seed in range(24):
+        rng = np.random.default_rng(1000 + seed)
+        h = random_tree(oracle, rng, depth=seed % 5)
+        A = oracle.full(h)
+        tree = to_product_tree(gpu, h)
+        k = 1 + seed % 4
+        X = rng.standard_normal((A.shape[1], k))
+        got = tree @ X
+        assert relerr(got, A @ X) <= TOL or np.linalg.norm(got - A @ X) <= 1e-13, seed
+        Xt = rng.standard_normal((A.shape[0], k))
+        got = tree._packed.tmatmul(Xt)
+        assert relerr(got, A.T @ Xt) <= TOL or np.linalg.norm(got - A.T @ Xt) <= 1e-13, seed
+        tree._packed.close()
+
+
 def test_golden_fixtures(gpu, oracle):
     import make_golden
     gdir = os.path.join(os.path.dirname(__file__), "golden")
