@@ -1241,9 +1241,11 @@ static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t r
       HSSB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
     }
   }
+  // every shard must cut the call into the same blocks (each block contains the exchange step)
+  const int64_t rows_eff = h->n_shards > 1 ? (h->m + h->n) / h->n_shards : rows_x + rows_y;
   int64_t cb = nrhs;
   if (h->pipeline_cols > 0) cb = std::min<int64_t>(nrhs, h->pipeline_cols);
-  else if (nrhs >= 16 && (int64_t)(rows_x + rows_y) * nrhs * 8 >= ((int64_t)64 << 20)) cb = std::max<int64_t>(8, ((nrhs + 7) / 8 + 7) / 8 * 8);  // ~8 blocks: measured best on PCIe Gen5 (tools/e2e_blocks.py)
+  else if (nrhs >= 16 && rows_eff * nrhs * 8 >= ((int64_t)64 << 20)) cb = std::max<int64_t>(8, ((nrhs + 7) / 8 + 7) / 8 * 8);  // ~8 blocks: measured best on PCIe Gen5 (tools/e2e_blocks.py)
   int64_t nblk = (nrhs + cb - 1) / cb;
   if (nblk > hssb_matrix::MAX_BLOCKS) { cb = (nrhs + hssb_matrix::MAX_BLOCKS - 1) / hssb_matrix::MAX_BLOCKS; nblk = (nrhs + cb - 1) / cb; }
   // copies of this call must not overtake the previous call's use of the staging buffers
