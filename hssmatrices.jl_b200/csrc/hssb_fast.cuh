@@ -640,9 +640,14 @@ static int launch_leaf_nt(hssb_matrix* H, const Phase& ph, const CallParams& cp,
 template <int M, int R>
 static int launch_leaf(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st, bool down) {
   constexpr int NTW = 8192 / M;  // widest tile: 64 right-hand sides for 128-row leaves, 32 for 256-row leaves
-  // with 64-wide tiles a last (or only) tile of <= 32 columns would waste half of the DMMA work
-  const int rem = cp.nrhs % 64;
-  const bool narrow = NTW > 32 && rem > 0 && rem <= 32 && cp.nrhs < 128;
+  // Few right-hand sides (e.g. nrhs = 20 in randcompress_adaptive, compression.jl:341): with wide
+  // tiles most of the DMMA work would be spent on empty columns and the product, HBM-bound at small
+  // nrhs, would become compute-bound.  Pick the narrowest tile that covers the last (or only) tile.
+  const int rem = cp.nrhs % 64 == 0 ? 64 : cp.nrhs % 64;
+  if constexpr (R >= 32) {
+    if (cp.nrhs <= 16) return down ? launch_leaf_nt<M, R, true, 16>(H, ph, cp, st) : launch_leaf_nt<M, R, false, 16>(H, ph, cp, st);
+  }
+  const bool narrow = NTW > 32 && rem <= 32 && cp.nrhs < 128;
   if (narrow) return down ? launch_leaf_nt<M, R, true, 32>(H, ph, cp, st) : launch_leaf_nt<M, R, false, 32>(H, ph, cp, st);
   return down ? launch_leaf_nt<M, R, true, NTW>(H, ph, cp, st) : launch_leaf_nt<M, R, false, NTW>(H, ph, cp, st);
 }
