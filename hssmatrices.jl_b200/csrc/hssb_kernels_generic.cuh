@@ -2,7 +2,8 @@
 // product.  Handles ragged leaves (62/63 rows), variable and zero ranks,
 // unbalanced trees, nrhs not a multiple of anything.  One CTA = one 64x64 tile
 // of one task's output; K is walked in 16-wide slabs staged through shared
-// memory with coalesced (unit-stride) global reads for both A layouts.
+// memory with coalesced (unit-stride) global reads for both A layouts; the next slab is
+// prefetched into registers while the current one is consumed.
 #pragma once
 
 #include "hssb_internal.h"
@@ -40,63 +41,76 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
 
-#pragma unroll 1
-  for (int s = 0; s < 2; ++s) {
-    const int K = s ? t.K1 : t.K0;
-    if (K <= 0) continue;
-    const double* A = p.pool + (s ? t.a1 : t.a0);
-    const int64_t lda = s ? t.lda1 : t.lda0;
-    const bool ta = s ? t.ta1 : t.ta0;
-    int64_t ldb;
-    const double* B = operand_b(p, s ? t.sb1 : t.sb0, s ? t.b1 : t.b0, s ? t.ldb1 : t.ldb0, ldb);
-
-    for (int k0 = 0; k0 < K; k0 += G_TK) {
-      // ---- stage A slab: As[kk][mm] = op(A)(m0+mm, k0+kk)
-      if (!ta) {
-        const int mm = tid & 63;
+  // The K loop runs over the slabs of both products back to back; the global loads of slab i+1
+  // are issued into registers before slab i is consumed from shared memory, so a level of small
+  // tasks (a few slabs each) pays the global-memory latency once instead of once per slab.
+  const int K0 = t.K0 > 0 ? t.K0 : 0, K1 = t.K1 > 0 ? t.K1 : 0;
+  const int nslab0 = (K0 + G_TK - 1) / G_TK, nslab = nslab0 + (K1 + G_TK - 1) / G_TK;
+  int64_t ldb0 = 0, ldb1 = 0;
+  const double* B0 = operand_b(p, t.sb0, t.b0, t.ldb0, ldb0);
+  const double* B1 = operand_b(p, t.sb1, t.b1, t.ldb1, ldb1);
+  double ra[4], rb[4];
+  auto fetch = [&](int slab) {
+    const bool s1 = slab >= nslab0;
+    const int K = s1 ? K1 : K0, k0 = (s1 ? slab - nslab0 : slab) * G_TK;
+    const double* A = p.pool + (s1 ? t.a1 : t.a0);
+    const int64_t lda = s1 ? t.lda1 : t.lda0;
+    const bool ta = s1 ? t.ta1 : t.ta0;
+    const double* B = s1 ? B1 : B0;
+    const int64_t ldb = s1 ? ldb1 : ldb0;
+    if (!ta) {
+      const int mm = tid & 63;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int kk = (tid >> 6) + 4 * r;
-          double v = 0.0;
-          if (m0 + mm < t.M && k0 + kk < K) v = A[(int64_t)(k0 + kk) * lda + (m0 + mm)];
-          As[kk][mm] = v;
-        }
-      } else {
-        const int kk = tid & 15;
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int mm = (tid >> 4) + 16 * r;
-          double v = 0.0;
-          if (m0 + mm < t.M && k0 + kk < K) v = A[(int64_t)(m0 + mm) * lda + (k0 + kk)];
-          As[kk][mm] = v;
-        }
+      for (int r = 0; r < 4; ++r) {
+        const int kk = (tid >> 6) + 4 * r;
+        ra[r] = (m0 + mm < t.M && k0 + kk < K) ? A[(int64_t)(k0 + kk) * lda + (m0 + mm)] : 0.0;
       }
-      // ---- stage B slab: Bs[kk][nn] = B(k0+kk, n0+nn)
-      {
-        const int kk = tid & 15;
+    } else {
+      const int kk = tid & 15;
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int nn = (tid >> 4) + 16 * r;
-          double v = 0.0;
-          if (n0 + nn < N && k0 + kk < K) v = B[(int64_t)(n0 + nn) * ldb + (k0 + kk)];
-          Bs[kk][nn] = v;
-        }
+      for (int r = 0; r < 4; ++r) {
+        const int mm = (tid >> 4) + 16 * r;
+        ra[r] = (m0 + mm < t.M && k0 + kk < K) ? A[(int64_t)(m0 + mm) * lda + (k0 + kk)] : 0.0;
       }
-      __syncthreads();
-#pragma unroll
-      for (int kk = 0; kk < G_TK; ++kk) {
-        double a[4], b[4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-#pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
-      }
-      __syncthreads();
     }
+    const int kk = tid & 15;
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int nn = (tid >> 4) + 16 * r;
+      rb[r] = (n0 + nn < N && k0 + kk < K) ? B[(int64_t)(n0 + nn) * ldb + (k0 + kk)] : 0.0;
+    }
+  };
+  auto stage = [&](int slab) {  // registers -> shared memory, same element mapping as fetch()
+    const bool ta = slab >= nslab0 ? t.ta1 : t.ta0;
+    if (!ta) {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) As[(tid >> 6) + 4 * r][tid & 63] = ra[r];
+    } else {
+#pragma unroll
+      for (int r = 0; r < 4; ++r) As[tid & 15][(tid >> 4) + 16 * r] = ra[r];
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) Bs[tid & 15][(tid >> 4) + 16 * r] = rb[r];
+  };
+
+  if (nslab > 0) fetch(0);
+  for (int slab = 0; slab < nslab; ++slab) {
+    stage(slab);
+    __syncthreads();
+    if (slab + 1 < nslab) fetch(slab + 1);
+#pragma unroll
+    for (int kk = 0; kk < G_TK; ++kk) {
+      double a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
   }
 
   // ---- epilogue
