@@ -106,11 +106,14 @@ struct StreamCfg {
   static constexpr int LDF = K1 + 4, LDA = MO + 4;
   static constexpr int XSLABS = K0 / 16;                 // X block = XSLABS boxes of {16 rows x NT cols}, 128B-swizzled
   static constexpr int XBUF = K0 * NT;                   // doubles per X buffer (dense)
+  // X blocks in flight: double buffered; the (memory-bound) leaf-up kernel with narrow tiles has few
+  // DMMAs per item, so it needs more items in flight to cover the load latency
+  static constexpr int XBUFS = DOWN ? 2 : (NT <= 16 ? 4 : ((NT <= 32 && M <= 128) ? 3 : 2));
   static constexpr int BAR_BYTES = 256;
-  static constexpr int FIXED_BYTES = BAR_BYTES + 8 * (2 * XBUF + (K1 ? NT * LDF : 0));
+  static constexpr int FIXED_BYTES = BAR_BYTES + 8 * (XBUFS * XBUF + (K1 ? NT * LDF : 0));
   static constexpr int STAGE_BYTES = 8 * KC * LDA;
   static constexpr int FIT = (232448 - FIXED_BYTES) / STAGE_BYTES;
-  static constexpr int NSTAGE = DOWN ? (FIT > 6 ? 6 : FIT) : 2;       // as deep a ring as shared memory allows
+  static constexpr int NSTAGE = DOWN ? (FIT > 6 ? 6 : FIT) : (FIT > XBUFS ? XBUFS : FIT);  // as deep a ring as shared memory allows
   // F(i) and the first slice of X(i+1) are issued after chunk CX of item i; by then every
   // consumer has left item i-1 (the producer can be at most NSTAGE chunks ahead), so the
   // waits on f_empty / x_empty never hold up the A ring.
@@ -120,7 +123,7 @@ struct StreamCfg {
   static_assert(MO % (8 * WR) == 0 && NT % (8 * WC) == 0 && TM >= 1 && TN >= 1, "warp tiling");
   static_assert(K0 % KC == 0 && K1 % KC == 0 && KC % 4 == 0 && NCH0 >= 1 && NSTAGE >= 2 && XPIECES >= 1 && K0 % 16 == 0, "chunking");
   static_assert(KSTEPS == 2 || KSTEPS % 4 == 0, "k-steps per chunk must be 2 or a multiple of 4 (swizzle bookkeeping)");
-  static_assert(SMEM <= 232448 && 2 * NSTAGE + 6 <= BAR_BYTES / 8, "shared memory budget");
+  static_assert(SMEM <= 232448 && 2 * NSTAGE + 2 * XBUFS + 2 <= BAR_BYTES / 8, "shared memory budget");
 };
 
 template <int M, int R, bool DOWN, int NT_>
@@ -132,12 +135,12 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + C::SMEM - C::BAR_BYTES);
   uint64_t* a_full = bars;                    // [NSTAGE]
   uint64_t* a_empty = bars + C::NSTAGE;       // [NSTAGE]
-  uint64_t* x_full = bars + 2 * C::NSTAGE;    // [2]
-  uint64_t* x_empty = x_full + 2;             // [2]
-  uint64_t* f_full = x_empty + 2;             // [1]
+  uint64_t* x_full = bars + 2 * C::NSTAGE;    // [XBUFS]
+  uint64_t* x_empty = x_full + C::XBUFS;      // [XBUFS]
+  uint64_t* f_full = x_empty + C::XBUFS;      // [1]
   uint64_t* f_empty = f_full + 1;             // [1]
   double* Xs = reinterpret_cast<double*>(smem_raw);                 // [2][XSLABS][NT][16], swizzled
-  double* Fs = Xs + 2 * C::XBUF;                                    // [NT][LDF]
+  double* Fs = Xs + C::XBUFS * C::XBUF;                             // [NT][LDF]
   double* As = Fs + (C::K1 ? C::NT * C::LDF : 0);                   // [NSTAGE][KC][LDA]
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -149,7 +152,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
 
   if (tid == 0) {
     for (int s = 0; s < C::NSTAGE; ++s) { mbar_init(&a_full[s], 1); mbar_init(&a_empty[s], C::NWARPS); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], C::NWARPS); }
+    for (int s = 0; s < C::XBUFS; ++s) { mbar_init(&x_full[s], 1); mbar_init(&x_empty[s], C::NWARPS); }
     mbar_init(f_full, 1);
     mbar_init(f_empty, C::NWARPS);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
@@ -172,9 +175,9 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
     // counted, so the expected byte count is always the full block.
     auto load_x = [&](int item, int piece, int npieces) {
       const GTask& tk = tasks[(first + item) / ntiles];
-      const int tile = (first + item) % ntiles, buf = item & 1;
+      const int tile = (first + item) % ntiles, buf = item % C::XBUFS;
       if (piece == 0) {
-        mbar_wait(&x_empty[buf], ((item >> 1) & 1) ^ 1);
+        mbar_wait(&x_empty[buf], ((item / C::XBUFS) & 1) ^ 1);
         if (lane == 0) mbar_expect_tx(&x_full[buf], (uint32_t)(C::XBUF * 8));
         __syncwarp();
       }
@@ -282,7 +285,8 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
   }
   const double* Abase = As + wr * (C::TM * 8) + gq + t * C::LDA;
   for (int item = 0; item < my; ++item) {
-    const int buf = item & 1;
+    const int buf = item % C::XBUFS, nbuf = (item + 1) % C::XBUFS;
+    const uint32_t nxpar = ((item + 1) / C::XBUFS) & 1;
     const bool more = item + 1 < my;
     // issue the loads the epilogue needs now; their latency hides behind the whole item
     const int task_i = (first + item) / ntiles, tile = (first + item) - task_i * ntiles;
@@ -298,7 +302,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
         nw.b0 = &a_full[nst]; nw.p0 = nph;
         if (last_x) {
           if (C::K1) { nw.b1 = f_full; nw.p1 = item & 1; }
-          else { nw.b1 = &x_full[buf ^ 1]; nw.p1 = ((item + 1) >> 1) & 1; }
+          else { nw.b1 = &x_full[nbuf]; nw.p1 = nxpar; }
         }
       }
       const bool ok = chunk(Abase + st * C::KC * C::LDA, Bx, std::true_type{}, c * C::KSTEPS, nw);
@@ -320,7 +324,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
         const bool last_f = c == C::NCH1 - 1;
         if (!dbg_nowait && (!last_f || more)) {
           nw.b0 = &a_full[nst]; nw.p0 = nph;
-          if (last_f) { nw.b1 = &x_full[buf ^ 1]; nw.p1 = ((item + 1) >> 1) & 1; }
+          if (last_f) { nw.b1 = &x_full[nbuf]; nw.p1 = nxpar; }
         }
         const bool ok = chunk(Abase + st * C::KC * C::LDA, Bf + c * C::KC, std::false_type{}, 0, nw);
         __syncwarp();
