@@ -186,6 +186,7 @@ def main():
     if not torch.cuda.is_available() or hb.device_count() < 1:
         raise SystemExit("bench.py needs a B200: the product path has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(torch, local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     N = world
@@ -339,7 +340,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["desc"], "n_total": n_total, "leafsize": ls, "rank": r, "nrhs": k,
                        "parallelism": f"subtree-shard x{N}" if N > 1 else "single GPU", "variant": args.variant,
-                       "exchange": exchange,
+                       "exchange": exchange, "host_numa_node": numa,
                        "l2": "working set (generators + X + Y = %.2f GB per GPU) >> 126 MB L2, no flush needed" % (bytes_local * 1e-9),
                        "cuda_graph": bool("nograph" not in variants)},
             "hbm_gbs": gbs,
@@ -365,6 +366,28 @@ def main():
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
+
+
+def bind_to_gpu_numa_node(torch, local):
+    """Pin this rank to the CPU cores of its GPU's NUMA node before any pinned host buffer is
+    allocated (first touch), so that the end-to-end leg does not cross sockets: with one rank per
+    GPU all eight PCIe links are busy at once and remote host memory becomes the bottleneck."""
+    try:
+        pr = torch.cuda.get_device_properties(local)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def profile_phases(hb, P, X, Y, rows, k, st, reps):
