@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", default="default", help="kernel variant switches: generic, nograph, nccl")
+    ap.add_argument("--variant", default="default", help="comma-separated switches: generic, nograph, nccl, adjoint (time Y = A' X)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = dict(CONFIGS[args.config])
@@ -244,8 +244,10 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    adjoint = "adjoint" in variants  # time Y = A' X (hssb_matmul_t_dev) instead of Y = A X
+
     def step():
-        P.matmul_dev(X.data_ptr(), rows, Y.data_ptr(), rows, k, 1.0, 0.0, stream=st)
+        P.matmul_dev(X.data_ptr(), rows, Y.data_ptr(), rows, k, 1.0, 0.0, stream=st, trans=adjoint)
 
     # ---------------- device-resident throughput (`value`) -------------------
     sampler = ClockSampler(local) if rank == 0 else None
@@ -278,7 +280,7 @@ def main():
     # Dominant kernel = the leaf-down kernel (Y = D X + U F: 2mk(m+r) of the 2mk(m+2r)+... flops).
     prof = None
     if rank == 0 or N > 1:
-        prof = profile_phases(hb, P, X, Y, rows, k, st, max(3, min(args.steps, 10)))
+        prof = profile_phases(hb, P, X, Y, rows, k, st, max(3, min(args.steps, 10)), adjoint)
 
     # ---------------- end to end through the host entry (`e2e`) ---------------
     e2e = None
@@ -289,11 +291,11 @@ def main():
         xs, ys = Xh.numpy().T, Yh.numpy().T  # column-major (rows x k) views of the pinned buffers
         steps_e = max(3, min(args.steps, 5))
         for _ in range(2):
-            P.mul_(ys, xs, 1.0, 0.0)
+            P.mul_(ys, xs, 1.0, 0.0, trans=adjoint)
         barrier()
         t0 = time.perf_counter()
         for _ in range(steps_e):
-            P.mul_(ys, xs, 1.0, 0.0)  # H2D of X, product, D2H of Y, synchronous
+            P.mul_(ys, xs, 1.0, 0.0, trans=adjoint)  # H2D of X, product, D2H of Y, synchronous
         barrier()
         te = torch.tensor([(time.perf_counter() - t0) / steps_e], dtype=torch.float64, device="cuda")
         if N > 1:
@@ -340,6 +342,7 @@ def main():
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["desc"], "n_total": n_total, "leafsize": ls, "rank": r, "nrhs": k,
                        "parallelism": f"subtree-shard x{N}" if N > 1 else "single GPU", "variant": args.variant,
+                       "operator": "A' (adjoint twin pool)" if adjoint and P.get_option(hb.OPT_ADJOINT_TWIN) == 2 else ("A'" if adjoint else "A"),
                        "exchange": exchange, "host_numa_node": numa,
                        "l2": "working set (generators + X + Y = %.2f GB per GPU) >> 126 MB L2, no flush needed" % (bytes_local * 1e-9),
                        "cuda_graph": bool("nograph" not in variants)},
@@ -390,7 +393,7 @@ def bind_to_gpu_numa_node(torch, local):
         return None
 
 
-def profile_phases(hb, P, X, Y, rows, k, st, reps):
+def profile_phases(hb, P, X, Y, rows, k, st, reps, trans=False):
     """Per-phase device times from CUDA events recorded by the library between
     its own launches on the launching stream (HSSB_OPT_PROFILE)."""
     import torch
@@ -399,7 +402,7 @@ def profile_phases(hb, P, X, Y, rows, k, st, reps):
     P.set_option(hb.OPT_USE_GRAPH, 0)
     acc = None
     for i in range(reps + 1):
-        P.matmul_dev(X.data_ptr(), rows, Y.data_ptr(), rows, k, 1.0, 0.0, stream=st)
+        P.matmul_dev(X.data_ptr(), rows, Y.data_ptr(), rows, k, 1.0, 0.0, stream=st, trans=trans)
         torch.cuda.synchronize()
         ph = P.phase_times()
         if i == 0:

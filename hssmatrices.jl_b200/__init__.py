@@ -113,9 +113,10 @@ SIGNATURES = {
     "hssb_debug_task": (C.c_int, [_P, _i64, C.POINTER(_TaskT)]),
     "hssb_debug_phase": (C.c_int, [_P, _i64, C.POINTER(_PhaseT)]),
     "hssb_debug_pool": (C.c_int, [_P, _P, _i64]),
+    "hssb_debug_pool_t": (C.c_int, [_P, _P, _i64]),
 }
 
-OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS = 1, 2, 4, 5, 6
+OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS, OPT_ADJOINT_TWIN = 1, 2, 4, 5, 6, 7
 PHASE_NAMES = ("leaf_up", "merge", "exchange", "translate", "leaf_down", "exchange_ack")
 KIND_NAMES = ("D", "U", "V", "B12", "B21", "R", "W")
 
@@ -567,12 +568,15 @@ class PackedHss:
         Cm = np.empty((self.info.local_m, B.shape[1]), order="F")
         return self.mul_(Cm, B, 1.0, 0.0)
 
-    def matmul_dev(self, x_ptr, ldx, y_ptr, ldy, nrhs, alpha=1.0, beta=0.0, stream=None, rows_x=None, rows_y=None):
-        """Asynchronous product on raw device pointers (the timed entry)."""
-        rows_x = self.info.local_n if rows_x is None else rows_x
-        rows_y = self.info.local_m if rows_y is None else rows_y
-        _check(lib().hssb_matmul_dev(self._h, rows_y, rows_x, nrhs, x_ptr, ldx, y_ptr, ldy, float(alpha), float(beta),
-                                     stream))
+    def matmul_dev(self, x_ptr, ldx, y_ptr, ldy, nrhs, alpha=1.0, beta=0.0, stream=None, rows_x=None, rows_y=None,
+                   trans=False):
+        """Asynchronous product on raw device pointers (the timed entry); trans=True applies A'."""
+        if rows_x is None:
+            rows_x = self.info.local_m if trans else self.info.local_n
+        if rows_y is None:
+            rows_y = self.info.local_n if trans else self.info.local_m
+        fn = lib().hssb_matmul_t_dev if trans else lib().hssb_matmul_dev
+        _check(fn(self._h, rows_y, rows_x, nrhs, x_ptr, ldx, y_ptr, ldy, float(alpha), float(beta), stream))
 
     # multi-GPU ---------------------------------------------------------------
     @staticmethod
@@ -598,6 +602,14 @@ class PackedHss:
         _check(lib().hssb_xchg_import(self._h, buf, len(blobs)))
 
     # plan export (tests) -------------------------------------------------------
+    def debug_pool_t(self):
+        """Image of the adjoint twin pool (uniform trees): the forward plan over it computes A' X."""
+        pl = _i64()
+        _check(lib().hssb_debug_counts(self._h, None, None, C.byref(pl)))
+        pool = np.zeros(pl.value)
+        _check(lib().hssb_debug_pool_t(self._h, _ptr(pool), pool.size))
+        return pool
+
     def debug_plan(self):
         nt, nph, pl = _i64(), _i64(), _i64()
         _check(lib().hssb_debug_counts(self._h, C.byref(nt), C.byref(nph), C.byref(pl)))

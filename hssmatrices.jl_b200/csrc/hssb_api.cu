@@ -640,6 +640,108 @@ static int ensure_workspace(hssb_matrix* H, int64_t nrhs) {
 }
 
 // BFS renumbering of the builder's post-order ids; node 0 becomes the root.
+// --------------------------------------------------------- adjoint twin pool ---
+// A' is the HSS matrix with generators D', U <-> V, B12 <-> B21', R <-> W (hssmatrix.jl:165-180).
+// On a uniform tree (square leaves, one rank) those blocks have the stored shapes of the blocks they
+// replace (V and W are stored transposed), so the twin pool keeps the layout of the primary pool
+// and every twin block is the transpose of one stored primary block.
+static inline int twin_partner(int kind) {
+  switch (kind) {
+    case BK_U: return BK_V;
+    case BK_V: return BK_U;
+    case BK_B12: return BK_B21;
+    case BK_B21: return BK_B12;
+    case BK_R: return BK_W;
+    case BK_W: return BK_R;
+    default: return BK_D;
+  }
+}
+
+static bool twin_blocks(const hssb_matrix* H, std::vector<TwinBlock>& out) {
+  out.clear();
+  if (!H->padded) return false;
+  for (auto& t : H->nodes)
+    for (int k = 0; k < BK_COUNT; ++k) {
+      const int s = twin_partner(k);
+      if ((t.off[k] < 0) != (t.off[s] < 0)) return false;
+      if (t.off[k] < 0) continue;
+      if (t.rows[k] != t.cols[s] || t.cols[k] != t.rows[s]) return false;
+      TwinBlock b;
+      b.src = t.off[s]; b.dst = t.off[k];
+      b.rows = (int32_t)t.rows[s]; b.cols = (int32_t)t.cols[s];
+      b.ld_src = t.ld[s]; b.ld_dst = t.ld[k];
+      out.push_back(b);
+    }
+  return true;
+}
+
+// One CTA per block (grid-stride), 32x32 tiles through shared memory: both sides coalesced.
+__global__ void __launch_bounds__(256)
+twin_transpose_kernel(const TwinBlock* __restrict__ blocks, int64_t nblocks, const double* __restrict__ pool,
+                      double* __restrict__ twin) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int64_t b = blockIdx.x; b < nblocks; b += gridDim.x) {
+    const TwinBlock tb = blocks[b];
+    const int tr = (tb.rows + 31) / 32, tc = (tb.cols + 31) / 32;
+    for (int t = 0; t < tr * tc; ++t) {
+      const int r0 = (t % tr) * 32, c0 = (t / tr) * 32;
+#pragma unroll
+      for (int j = ty; j < 32; j += 8)
+        if (r0 + tx < tb.rows && c0 + j < tb.cols) tile[j][tx] = pool[tb.src + (int64_t)(c0 + j) * tb.ld_src + r0 + tx];
+      __syncthreads();
+#pragma unroll
+      for (int j = ty; j < 32; j += 8)  // dst(c, r) = src(r, c): dst column r0 + j, dst row c0 + tx
+        if (c0 + tx < tb.cols && r0 + j < tb.rows) twin[tb.dst + (int64_t)(r0 + j) * tb.ld_dst + c0 + tx] = tile[tx][j];
+      __syncthreads();
+    }
+  }
+}
+
+// 0: the twin is ready, 1: not available (caller falls back to the any-shape transposed plan), < 0: error
+static int ensure_twin(hssb_matrix* H) {
+  if (H->pool_t_dev) return 0;
+  if (!H->adjoint_twin || H->twin_unavailable) return 1;
+  std::vector<TwinBlock> tb;
+  if (!twin_blocks(H, tb) || tb.empty()) { H->twin_unavailable = true; return 1; }
+  size_t free_b = 0, total_b = 0;
+  const size_t need = (size_t)H->pool_len * sizeof(double);
+  if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || free_b < need + ((size_t)1 << 30)) {  // keep 1 GiB for workspaces / staging
+    cudaGetLastError();
+    H->twin_unavailable = true;
+    return 1;
+  }
+  if (cudaMalloc(&H->pool_t_dev, need) != cudaSuccess) {
+    cudaGetLastError();
+    H->pool_t_dev = nullptr;
+    H->twin_unavailable = true;
+    return 1;
+  }
+  TwinBlock* dtb = nullptr;
+  auto fail = [&]() { cudaFree(dtb); cudaFree(H->pool_t_dev); H->pool_t_dev = nullptr; };
+  cudaError_t e = cudaMalloc(&dtb, tb.size() * sizeof(TwinBlock));
+  if (e == cudaSuccess) e = cudaMemsetAsync(H->pool_t_dev, 0, need, H->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(dtb, tb.data(), tb.size() * sizeof(TwinBlock), cudaMemcpyHostToDevice, H->stream);
+  if (e == cudaSuccess) {
+    const int grid = (int)std::min<size_t>(tb.size(), 148 * 8);
+    twin_transpose_kernel<<<grid, 256, 0, H->stream>>>(dtb, (int64_t)tb.size(), H->pool_dev, H->pool_t_dev);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(H->stream);
+  if (e != cudaSuccess) {
+    fail();
+    HSSB_FAIL(HSSB_ERR_CUDA, "building the adjoint twin pool failed: %s", cudaGetErrorString(e));
+  }
+  cudaFree(dtb);
+  return 0;
+}
+
+static void drop_twin(hssb_matrix* H) {
+  if (H->pool_t_dev) cudaFree(H->pool_t_dev);
+  H->pool_t_dev = nullptr;
+  H->twin_unavailable = false;
+}
+
 static void nodes_from_builder(const hssb_builder* b, int64_t root, hssb_matrix* H, std::vector<BlockSource>& src) {
   std::vector<int64_t> order{root};
   for (size_t q = 0; q < order.size(); ++q) {
@@ -1092,6 +1194,7 @@ int hssb_destroy(hssb_matrix* h) {
     }
   cudaFree(h->my_flags);
   cudaFree(h->pool_dev);
+  cudaFree(h->pool_t_dev);
   cudaFree(h->tasks_dev);
   cudaFree(h->z_dev);
   cudaFree(h->f_dev);
@@ -1166,10 +1269,20 @@ int hssb_reserve(hssb_matrix* h, int64_t max_nrhs) {
   return ensure_workspace(h, max_nrhs);
 }
 
+// How Y = A' X runs: 0 = forward plan over the adjoint twin pool, 1 = any-shape transposed task
+// table over the primary pool (single shard only), < 0 = error.
+static int select_adjoint(hssb_matrix* h) {
+  const int tw = ensure_twin(h);
+  if (tw < 0) return tw;
+  if (tw == 1 && h->n_shards != 1)
+    HSSB_FAIL(HSSB_ERR_STATE, "the transposed product of a sharded matrix needs the adjoint twin pool "
+                              "(uniform tree, HSSB_OPT_ADJOINT_TWIN = 1 and room for a second pool on the device)");
+  return tw;
+}
+
 static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* dX, int64_t ldx,
                            double* dY, int64_t ldy, double alpha, double beta, void* stream) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
-  if (trans && h->n_shards != 1) HSSB_FAIL(HSSB_ERR_STATE, "the transposed product is not available on a sharded matrix");
   // DimensionMismatch checks of matmul.jl:19-20 (for A' the roles of the two dimensions swap)
   const int64_t need_x = trans ? h->local_m : h->local_n, need_y = trans ? h->local_n : h->local_m;
   if (rows_x != need_x)
@@ -1187,9 +1300,15 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
   if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
   int rc = ensure_workspace(h, nrhs);
   if (rc) return rc;
+  const double* pool = h->pool_dev;
+  if (trans) {
+    rc = select_adjoint(h);
+    if (rc < 0) return rc;
+    if (rc == 0) { pool = h->pool_t_dev; trans = 0; }  // A' X = the forward plan over the twin pool
+  }
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   CallParams cp;
-  cp.pool = h->pool_dev; cp.X = dX; cp.Y = dY; cp.Z = h->z_dev; cp.F = h->f_dev;
+  cp.pool = pool; cp.X = dX; cp.Y = dY; cp.Z = h->z_dev; cp.F = h->f_dev;
   cp.ldx = ldx; cp.ldy = ldy; cp.nrhs = (int32_t)nrhs; cp.alpha = alpha; cp.beta = beta; cp.debug = h->debug_mode; cp.trans = trans;
   // graph replay: always for the host entry (its staging pointers are stable), on request for
   // caller-owned device pointers (a new pointer set costs a capture + instantiate)
@@ -1200,7 +1319,6 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
 static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx,
                             double* Y, int64_t ldy, double alpha, double beta) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
-  if (trans && h->n_shards != 1) HSSB_FAIL(HSSB_ERR_STATE, "the transposed product is not available on a sharded matrix");
   const int64_t need_x = trans ? h->local_m : h->local_n, need_y = trans ? h->local_n : h->local_m;
   if (rows_x != need_x)
     HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: first dimension of B (%lld) does not match second dimension of A (%lld)",
@@ -1215,6 +1333,10 @@ static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t r
   if ((rows_x > 0 && !X) || !Y) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL matrix pointer");
   DeviceGuard dg(h->device);
   if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
+  if (trans) {  // fail before any copy is queued
+    const int a = select_adjoint(h);
+    if (a < 0) return a;
+  }
   if (nrhs > h->stage_nrhs) {
     cudaFree(h->x_stage); cudaFree(h->y_stage);
     h->x_stage = h->y_stage = nullptr; h->stage_nrhs = 0;
@@ -1314,11 +1436,16 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
     case HSSB_OPT_PROFILE: h->profile = value != 0; break;
     case HSSB_OPT_DEBUG: h->debug_mode = (int)value; break;
     case HSSB_OPT_PIPELINE_COLS: h->pipeline_cols = value; break;
+    case HSSB_OPT_ADJOINT_TWIN: h->adjoint_twin = value != 0; break;
     default: HSSB_FAIL(HSSB_ERR_ARG, "hssb_set_option: unknown option %d", opt);
   }
   if (h->device < 0) return HSSB_OK;
   DeviceGuard dg(h->device);
   invalidate_graphs(h);
+  if (opt == HSSB_OPT_ADJOINT_TWIN) {  // 0 releases the twin, 1 lets the next transposed product (re)build it
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    drop_twin(h);
+  }
   return HSSB_OK;
 }
 
@@ -1328,6 +1455,9 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
     case HSSB_OPT_FORCE_GENERIC: return h->force_generic;
     case HSSB_OPT_USE_GRAPH: return h->use_graph;
     case HSSB_OPT_PROFILE: return h->profile;
+    case HSSB_OPT_DEBUG: return h->debug_mode;
+    case HSSB_OPT_PIPELINE_COLS: return h->pipeline_cols;
+    case HSSB_OPT_ADJOINT_TWIN: return !h->adjoint_twin ? 0 : (h->pool_t_dev ? 2 : 1);  // 2: built and in use
     default: return -1;
   }
 }
@@ -1597,6 +1727,26 @@ int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len) {
   if (h->device < 0 || !h->pool_dev) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_pool: no pool image");
   DeviceGuard dg(h->device);
   HSSB_CUDA(cudaMemcpy(out, h->pool_dev, (size_t)h->pool_len * 8, cudaMemcpyDeviceToHost));
+  return HSSB_OK;
+}
+
+// Host image of the adjoint twin pool (what ensure_twin builds on the device), for plan-only and
+// device handles alike: CPU tests run the FORWARD plan over it and must obtain A' X.
+int hssb_debug_pool_t(const hssb_matrix* h, double* out, int64_t len) {
+  if (!h || !out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_pool_t: NULL argument");
+  if (len < h->pool_len) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_pool_t: need %lld doubles", (long long)h->pool_len);
+  std::vector<TwinBlock> tb;
+  if (!twin_blocks(h, tb)) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_pool_t: the tree is not uniform, there is no adjoint twin");
+  if (h->device >= 0 && h->pool_t_dev) {
+    DeviceGuard dg(h->device);
+    HSSB_CUDA(cudaMemcpy(out, h->pool_t_dev, (size_t)h->pool_len * 8, cudaMemcpyDeviceToHost));
+    return HSSB_OK;
+  }
+  if (h->pool_host.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_pool_t: no twin on the device yet and no host pool image");
+  memset(out, 0, (size_t)h->pool_len * 8);
+  for (const TwinBlock& b : tb)
+    for (int64_t c = 0; c < b.cols; ++c)
+      for (int64_t r = 0; r < b.rows; ++r) out[b.dst + r * b.ld_dst + c] = h->pool_host[(size_t)(b.src + c * b.ld_src + r)];
   return HSSB_OK;
 }
 

@@ -88,6 +88,12 @@ struct Node {
   int32_t ldz = 0, ldf = 0;
 };
 
+// One block of the adjoint twin pool: twin[dst] (cols x rows, ld_dst) = pool[src] (rows x cols, ld_src) transposed.
+struct TwinBlock {
+  int64_t src, dst;
+  int32_t rows, cols, ld_src, ld_dst;
+};
+
 enum PhaseKind : int { PH_LEAF_UP = 0, PH_MERGE, PH_EXCHANGE, PH_TRANSLATE, PH_LEAF_DOWN, PH_XCHG_ACK };
 
 struct Phase {
@@ -113,6 +119,12 @@ struct hssb_matrix {
   hssb::GTask* tasks_dev = nullptr;
   double* pool_dev = nullptr;
   std::vector<double> pool_host;  // plan-only handles (CPU tests): host image of the pool
+  // Adjoint twin (uniform trees): a second pool of identical layout holding the generators of A'
+  // (D', U <-> V, B12 <-> B21', R <-> W), built on the device at the first transposed product so
+  // that A' X runs the forward plan and the fixed-shape kernels.  HSSB_OPT_ADJOINT_TWIN.
+  double* pool_t_dev = nullptr;
+  bool adjoint_twin = true;
+  bool twin_unavailable = false;  // not eligible or did not fit: the any-shape transposed plan is used
   int64_t pool_len = 0;  // doubles
   int64_t gen_elems = 0, flops_per_rhs = 0;
   int64_t z_rows = 0, f_rows = 0;

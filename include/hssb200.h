@@ -154,11 +154,16 @@ int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
 int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
                     const double* dX, int64_t ldx, double* dY, int64_t ldy, double alpha, double beta,
                     void* stream);
-/* Transposed product Y = alpha * A' * X + beta * Y on the SAME packed generators: what
- * `*(A::AbstractMatrix, hssB)` (matmul.jl:14) and `hssA' * X` need.  The reference builds a full
- * copied adjoint HssMatrix (hssmatrix.jl:165-171) on every such call; here the adjoint is a second
- * task table over the same pool.  rows_x must be size(A,1), rows_y size(A,2).  Single shard only;
- * runs on the any-shape kernel.                                                                   */
+/* Transposed product Y = alpha * A' * X + beta * Y: what `*(A::AbstractMatrix, hssB)` (matmul.jl:14)
+ * and `hssA' * X` need.  The reference builds a full copied adjoint HssMatrix (hssmatrix.jl:165-171)
+ * on EVERY such call.  Here:
+ *  - uniform trees (the fixed-shape kernel shapes): the first transposed product builds, on the
+ *    device, an adjoint twin pool of identical layout (D', U <-> V, B12 <-> B21', R <-> W) and A' X
+ *    then runs the forward plan and the DMMA kernels over it, sharded handles included.  Costs a
+ *    second pool of device memory; HSSB_OPT_ADJOINT_TWIN = 0 turns it off, and it is skipped when
+ *    the device cannot hold it;
+ *  - otherwise: a second task table over the SAME pool on the any-shape kernel (single shard only).
+ * rows_x must be size(A,1), rows_y size(A,2).                                                     */
 int hssb_matmul_t(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
                   const double* X, int64_t ldx, double* Y, int64_t ldy, double alpha, double beta);
 int hssb_matmul_t_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
@@ -173,6 +178,8 @@ int hssb_sync(hssb_matrix* h);
 #define HSSB_OPT_DEBUG 5         /* measurement only (library built with make DEBUG_MODES=1), WRONG RESULTS: bit 0 = leaf kernels compute on whatever is in
                                     shared memory without waiting for data, bit 1 = move data without computing */
 #define HSSB_OPT_PIPELINE_COLS 6 /* host entry: right-hand sides per pipelined block (0 = automatic)  */
+#define HSSB_OPT_ADJOINT_TWIN 7  /* 1 (default): hssb_matmul_t of a uniform tree keeps a transposed twin of the pool on the device;
+                                    0: release it / never build it.  hssb_get_option returns 2 once the twin exists. */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
@@ -238,6 +245,7 @@ int hssb_debug_counts(const hssb_matrix* h, int64_t* n_tasks, int64_t* n_phases,
 int hssb_debug_task(const hssb_matrix* h, int64_t i, hssb_task_t* out);
 int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* out);
 int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len);
+int hssb_debug_pool_t(const hssb_matrix* h, double* out, int64_t len); /* image of the adjoint twin pool */
 
 #ifdef __cplusplus
 }

@@ -10,9 +10,12 @@ PH_LEAF_UP, PH_MERGE, PH_EXCHANGE, PH_TRANSLATE, PH_LEAF_DOWN = range(5)
 
 
 class ShardState:
-    def __init__(self, packed, X, Y, nrhs):
+    def __init__(self, packed, X, Y, nrhs, pool=None):
         self.packed = packed
         self.tasks, self.phases, self.pool = packed.debug_plan()
+        if pool is not None:  # e.g. the adjoint twin pool: same layout, same plan
+            assert pool.shape == self.pool.shape
+            self.pool = pool
         self.nrhs = nrhs
         self.X = np.asfortranarray(X)
         self.Y = Y
@@ -59,9 +62,9 @@ class ShardState:
             self.run_task(self.tasks[i], alpha, beta)
 
 
-def run_plan(packed, X, Y, alpha=1.0, beta=0.0, trans=False):
+def run_plan(packed, X, Y, alpha=1.0, beta=0.0, trans=False, pool=None):
     """Single-shard plan: Y (in place) = alpha*op(A)*X + beta*Y, op(A) = A' if trans."""
-    st = ShardState(packed, X, Y, X.shape[1])
+    st = ShardState(packed, X, Y, X.shape[1], pool)
     for ph in st.phases:
         if bool(ph.transposed) != bool(trans):
             continue
@@ -70,11 +73,12 @@ def run_plan(packed, X, Y, alpha=1.0, beta=0.0, trans=False):
     return Y
 
 
-def run_sharded(packs, Xs, Ys, alpha=1.0, beta=0.0):
+def run_sharded(packs, Xs, Ys, alpha=1.0, beta=0.0, pools=None):
     """P plans in lockstep; the exchange phase is an all-gather of each shard's
     own slot of the exchange buffer."""
     nrhs = Xs[0].shape[1]
-    sts = [ShardState(p, x, y, nrhs) for p, x, y in zip(packs, Xs, Ys)]
+    pools = pools or [None] * len(packs)
+    sts = [ShardState(p, x, y, nrhs, pl) for p, x, y, pl in zip(packs, Xs, Ys, pools)]
     for s in sts:
         s.phases = [ph for ph in s.phases if not ph.transposed]
     nph = len(sts[0].phases)

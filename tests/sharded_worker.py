@@ -19,7 +19,9 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl" if torch.cuda.is_available() else "gloo")
     n, ls, r, k, seed = 8192, 128, 32, 64, 17
-    ref = o.matmul(o.synthetic_hss(n, ls, r, seed), o.synth_x(seed, n, k))
+    hs = o.synthetic_hss(n, ls, r, seed)
+    ref = o.matmul(hs, o.synth_x(seed, n, k))
+    ref_t = o.matmul(o.adjoint(hs), o.synth_x(seed, n, k))
     err = 0.0
     for mode in ("nccl", "peer"):
         P = hb.synthetic(n, ls, r, seed, device=local, shard_rank=rank, n_shards=world)
@@ -38,6 +40,13 @@ def main():
         for rep in range(3):    # repeated products exercise the epoch / acknowledgement protocol
             Y = P @ X
             err = max(err, np.linalg.norm(Y - mine) / np.linalg.norm(mine))
+        # A' X on the sharded handle: forward plan (same exchange) over the adjoint twin pool
+        mine_t = ref_t[P.info.local_col0:P.info.local_col0 + P.info.local_n]
+        for rep in range(2):
+            Yt = P.tmatmul(X)
+            err = max(err, np.linalg.norm(Yt - mine_t) / np.linalg.norm(mine_t))
+        Y = P @ X
+        err = max(err, np.linalg.norm(Y - mine) / np.linalg.norm(mine))
         dist.barrier()
         P.close()
     t = torch.tensor([err], device="cuda")

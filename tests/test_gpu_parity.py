@@ -93,13 +93,28 @@ def test_transposed_product(gpu, oracle):
     # forward product still right after a transposed one (the two plans share the workspaces)
     Xf = rng.standard_normal((333, 3))
     assert relerr(tree @ Xf, oracle.matmul(h, Xf)) <= TOL
-    # uniform synthetic tree (padded TMA-ready layout): transposed apply through the any-shape kernel
-    n, ls, r, seed = 2048, 128, 32, 9
-    hs = oracle.synthetic_hss(n, ls, r, seed)
-    Xs = rng.standard_normal((n, 5))
-    with gpu.synthetic(n, ls, r, seed) as Ps:
-        assert relerr(Ps.tmatmul(Xs), oracle.matmul(oracle.adjoint(hs), Xs)) <= TOL
-        assert relerr(Ps @ Xs, oracle.matmul(hs, Xs)) <= TOL
+    assert P.get_option(gpu.OPT_ADJOINT_TWIN) == 1    # not a uniform tree: no twin was built
+    # uniform synthetic trees (padded TMA-ready layout): the first transposed product builds the adjoint
+    # twin pool and A' X runs the forward plan / fixed-shape kernels over it; with the option off it
+    # runs the any-shape transposed task table over the primary pool
+    for n, ls, r, k, seed in ((2048, 128, 32, 5, 9), (4096, 256, 64, 33, 10), (2048, 128, 16, 64, 11)):
+        hs = oracle.synthetic_hss(n, ls, r, seed)
+        Xs = rng.standard_normal((n, k))
+        ref_t, ref_f = oracle.matmul(oracle.adjoint(hs), Xs), oracle.matmul(hs, Xs)
+        with gpu.synthetic(n, ls, r, seed) as Ps:
+            assert relerr(Ps.tmatmul(Xs), ref_t) <= TOL
+            assert Ps.get_option(gpu.OPT_ADJOINT_TWIN) == 2
+            assert relerr(Ps @ Xs, ref_f) <= TOL
+            C1 = rng.standard_normal((n, k))
+            got = Ps.mul_(np.asfortranarray(C1.copy()), Xs, 2.0, -1.0, trans=True)
+            assert relerr(got, 2.0 * ref_t - C1) <= TOL
+            twin = Ps.debug_pool_t()                  # device-built twin == host transposition of the pool
+            Ps.set_option(gpu.OPT_ADJOINT_TWIN, 0)
+            assert Ps.get_option(gpu.OPT_ADJOINT_TWIN) == 0
+            assert relerr(Ps.tmatmul(Xs), ref_t) <= TOL
+            assert relerr(Ps @ Xs, ref_f) <= TOL
+        with gpu.synthetic(n, ls, r, seed, plan_only=True) as Pp:
+            assert np.array_equal(twin, Pp.debug_pool_t())
 
 
 def test_save_load_device(gpu, oracle, tmp_path):
@@ -295,6 +310,17 @@ def test_full_size_config3_properties(gpu, oracle):
         torch.cuda.synchronize()
         lin = 0.5 * Y1 - 2.0 * Y2
         assert (torch.linalg.norm(Y3 - lin) / torch.linalg.norm(lin)).item() <= TOL
+        # (c) adjoint identity <X2, A X1> = <A' X2, X1> (A' through the adjoint twin pool), and the twin
+        # against the any-shape transposed task table over the primary pool
+        P.matmul_dev(X2.data_ptr(), n, Y2.data_ptr(), n, k, stream=st, trans=True)
+        torch.cuda.synchronize()
+        assert P.get_option(gpu.OPT_ADJOINT_TWIN) == 2
+        lhs, rhs = (X2 * Y1).sum().item(), (Y2 * X1).sum().item()
+        assert abs(lhs - rhs) <= TOL * (torch.linalg.norm(X2) * torch.linalg.norm(Y1)).item()
+        P.set_option(gpu.OPT_ADJOINT_TWIN, 0)
+        P.matmul_dev(X2.data_ptr(), n, Y3.data_ptr(), n, k, stream=st, trans=True)
+        torch.cuda.synchronize()
+        assert (torch.linalg.norm(Y3 - Y2) / torch.linalg.norm(Y2)).item() <= TOL
         # fixed-shape kernels vs the generic kernel on the same dense input
         P.set_option(gpu.OPT_FORCE_GENERIC, 1)
         P.matmul_dev(X1.data_ptr(), n, Y2.data_ptr(), n, k, stream=st)

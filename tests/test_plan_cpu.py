@@ -104,6 +104,43 @@ def test_transposed_plan(hb, oracle, n, leafsize, nrhs, rmin, rmax):
     assert relerr(Y, 0.3 * ref + 2.0 * C0) <= TOL
 
 
+@pytest.mark.parametrize("ls,r", [(128, 16), (256, 32)])
+def test_adjoint_twin_pool(hb, oracle, ls, r):
+    """Uniform trees: the FORWARD plan over the adjoint twin pool (D', U <-> V, B12 <-> B21', R <-> W,
+    hssmatrix.jl:165-180) is A' X, single shard and sharded, so hssb_matmul_t runs the fixed-shape kernels."""
+    n, seed, k = 16 * ls, 17, 3
+    h = oracle.synthetic_hss(n, ls, r, seed)
+    X = oracle.synth_x(seed, n, k)
+    ref = oracle.matmul(oracle.adjoint(h), X)
+    assert relerr(ref, oracle.full(h).T @ X) <= TOL
+    P = hb.synthetic(n, ls, r, seed, plan_only=True)
+    twin = P.debug_pool_t()
+    Y = np.full((n, k), np.nan, order="F")
+    plan_interp.run_plan(P, X, Y, pool=twin)
+    assert relerr(Y, ref) <= TOL
+    # the twin of the twin is the pool itself
+    _, _, pool = P.debug_plan()
+    assert not np.array_equal(pool, twin)
+    for P_ in (2, 4):
+        packs = [hb.synthetic(n, ls, r, seed, shard_rank=g, n_shards=P_, plan_only=True) for g in range(P_)]
+        rows = n // P_
+        Xs = [X[g * rows:(g + 1) * rows] for g in range(P_)]
+        Ys = [np.full((rows, k), np.nan, order="F") for _ in range(P_)]
+        plan_interp.run_sharded(packs, Xs, Ys, 0.5, 0.0, pools=[p.debug_pool_t() for p in packs])
+        assert relerr(np.vstack(Ys), 0.5 * ref) <= TOL
+
+
+def test_adjoint_twin_needs_uniform_tree(hb, oracle):
+    rng = np.random.default_rng(8)
+    cl = oracle.bisection_cluster(300, 40)
+    P = hb.pack(to_product_tree(hb, oracle.random_hss(cl, cl, rng, 1, 5)), plan_only=True)
+    with pytest.raises(hb.HssbError):
+        P.debug_pool_t()
+    Q = hb.synthetic(1024, 64, 4, 1, plan_only=True)   # uniform, but not a fixed-shape kernel shape
+    with pytest.raises(hb.HssbError):
+        Q.debug_pool_t()
+
+
 def test_subblock_is_rooted(hb, oracle):
     """matmul.jl:24: multiplying a sub-block ignores its own translators."""
     rng = np.random.default_rng(3)
