@@ -62,6 +62,10 @@ class _PhaseTime(C.Structure):
         "kind", "level", "top", "fast", "ntasks", "flops_per_rhs", "gen_elems", "x_rows", "y_rows")] + [("ms", C.c_double)]
 
 
+class _UlvInfo(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("supported", "factored", "pool_bytes", "flops_per_rhs", "z_rows", "f_rows")]
+
+
 class _PhaseT(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "kind", "task0", "ntasks", "maxM", "level", "top", "fast", "xchg_zoff", "xchg_slot_rows", "transposed")]
@@ -114,6 +118,12 @@ SIGNATURES = {
     "hssb_debug_phase": (C.c_int, [_P, _i64, C.POINTER(_PhaseT)]),
     "hssb_debug_pool": (C.c_int, [_P, _P, _i64]),
     "hssb_debug_pool_t": (C.c_int, [_P, _P, _i64]),
+    "hssb_ulv_factor": (C.c_int, [_P]),
+    "hssb_solve": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64]),
+    "hssb_solve_dev": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64, _P]),
+    "hssb_ulv_info": (C.c_int, [_P, _P]),
+    "hssb_debug_ulv_factor_host": (C.c_int, [_P]),
+    "hssb_debug_ulv_pool": (C.c_int, [_P, _P, _i64]),
 }
 
 OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS, OPT_ADJOINT_TWIN = 1, 2, 4, 5, 6, 7
@@ -567,6 +577,41 @@ class PackedHss:
             return (self @ B.reshape(-1, 1)).reshape(-1)
         Cm = np.empty((self.info.local_m, B.shape[1]), order="F")
         return self.mul_(Cm, B, 1.0, 0.0)
+
+    # the solver: hssA \ B (src/hssmatrix.jl:234 -> ulvfactsolve, src/ulvfactor.jl:10-19) ------------
+    @property
+    def ulv_info(self):
+        o = _UlvInfo()
+        _check(lib().hssb_ulv_info(self._h, C.byref(o)))
+        return o
+
+    def ulv_factor(self):
+        """Implicit ULV factorisation on the device (done once; solve() does it on first use)."""
+        _check(lib().hssb_ulv_factor(self._h))
+
+    def solve(self, B):
+        """`hssA \\ B` with host (numpy) arrays; returns a new column-major array."""
+        B = _f64(B)
+        if B.ndim == 1:
+            return self.solve(B.reshape(-1, 1)).reshape(-1)
+        Bf = _fcol(B)
+        Z = np.empty((self.info.n, B.shape[1]), order="F")
+        _check(lib().hssb_solve(self._h, Bf.shape[0], Bf.shape[1], _ptr(Bf), max(Bf.shape[0], 1), _ptr(Z), max(Z.shape[0], 1)))
+        return Z
+
+    ulvfactsolve = solve
+
+    def solve_dev(self, b_ptr, ldb, z_ptr, ldz, nrhs, stream=None):
+        """Asynchronous solve on raw device pointers."""
+        _check(lib().hssb_solve_dev(self._h, self.info.n, nrhs, b_ptr, ldb, z_ptr, ldz, stream))
+
+    def debug_ulv_pool(self, factor_on_host=False):
+        """Factor pool image (tests).  factor_on_host: plan-only handles run the node routine on the host first."""
+        if factor_on_host:
+            _check(lib().hssb_debug_ulv_factor_host(self._h))
+        pool = np.zeros(self.ulv_info.pool_bytes // 8)
+        _check(lib().hssb_debug_ulv_pool(self._h, _ptr(pool), pool.size))
+        return pool
 
     def matmul_dev(self, x_ptr, ldx, y_ptr, ldy, nrhs, alpha=1.0, beta=0.0, stream=None, rows_x=None, rows_y=None,
                    trans=False):

@@ -21,6 +21,7 @@
 #include "hssb_kernels_generic.cuh"
 #include "hssb_synth.cuh"
 #include "hssb_fast.cuh"
+#include "hssb_ulv.cuh"
 
 namespace hssb {
 
@@ -444,6 +445,10 @@ static void build_plan(hssb_matrix* H) {
   add_phase(H, PH_LEAF_DOWN, 0, false, batch);
 }
 
+}  // namespace hssb
+#include "hssb_ulv_plan.cuh"
+namespace hssb {
+
 static void detect_uniform(hssb_matrix* H) {
   // Fast fixed-shape kernels need: a perfect local tree, square leaves of one
   // size, one rank everywhere (rows and columns).
@@ -496,7 +501,7 @@ static int plan_matrix(hssb_matrix* H) {
   build_plan(H);
   plan_fast_phases(H);
   build_plan_transposed(H);
-
+  build_plan_ulv(H);
   return HSSB_OK;
 }
 
@@ -619,27 +624,32 @@ static int finish_matrix(hssb_matrix* H, const std::vector<BlockSource>* src, FI
   return HSSB_OK;
 }
 
-static int ensure_workspace(hssb_matrix* H, int64_t nrhs) {
-  if (nrhs <= H->ws_nrhs) return HSSB_OK;
+// The ULV solve needs more workspace rows per node than the product (zloc + [b; u] against Z); the
+// larger layout is only allocated once a solve asks for it.
+static int ensure_workspace(hssb_matrix* H, int64_t nrhs, bool ulv = false) {
+  if (nrhs <= H->ws_nrhs && (!ulv || H->ws_ulv)) return HSSB_OK;
   if (H->xchg_exported)
     HSSB_FAIL(HSSB_ERR_STATE, "the Z workspace is mapped by peer ranks: hssb_reserve(max_nrhs) before hssb_xchg_export (have %lld, need %lld)",
               (long long)H->ws_nrhs, (long long)nrhs);
+  ulv = ulv || H->ws_ulv;
+  nrhs = std::max(nrhs, H->ws_nrhs);
   if (H->z_dev) cudaFree(H->z_dev);
   if (H->f_dev) cudaFree(H->f_dev);
   H->z_dev = H->f_dev = nullptr;
   H->ws_nrhs = 0;
-  const size_t zb = (size_t)H->z_rows * (size_t)nrhs * sizeof(double);
-  const size_t fb = (size_t)H->f_rows * (size_t)nrhs * sizeof(double);
+  H->ws_ulv = false;
+  const size_t zb = (size_t)std::max(H->z_rows, ulv ? H->ulv_z_rows : 0) * (size_t)nrhs * sizeof(double);
+  const size_t fb = (size_t)std::max(H->f_rows, ulv ? H->ulv_f_rows : 0) * (size_t)nrhs * sizeof(double);
   if (cudaMalloc(&H->z_dev, zb) != cudaSuccess || cudaMalloc(&H->f_dev, fb) != cudaSuccess) {
     cudaGetLastError();
     HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of the Z/F workspaces (%.3f GB) failed", (zb + fb) * 1e-9);
   }
   H->ws_nrhs = nrhs;
+  H->ws_ulv = ulv;
   invalidate_graphs(H);
   return HSSB_OK;
 }
 
-// BFS renumbering of the builder's post-order ids; node 0 becomes the root.
 // --------------------------------------------------------- adjoint twin pool ---
 // A' is the HSS matrix with generators D', U <-> V, B12 <-> B21', R <-> W (hssmatrix.jl:165-180).
 // On a uniform tree (square leaves, one rank) those blocks have the stored shapes of the blocks they
@@ -947,7 +957,7 @@ static int launch_generic(hssb_matrix* H, const Phase& ph, const CallParams& cp,
 }
 
 static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
-  const std::vector<Phase>& phases = cp.trans ? H->phases_t : H->phases;
+  const std::vector<Phase>& phases = cp.trans == 2 ? H->phases_u : cp.trans ? H->phases_t : H->phases;
   const bool prof = H->profile && !cp.trans;
   if (prof) {
     while (H->prof_events.size() < H->phases.size() + 1) {
@@ -1195,6 +1205,7 @@ int hssb_destroy(hssb_matrix* h) {
   cudaFree(h->my_flags);
   cudaFree(h->pool_dev);
   cudaFree(h->pool_t_dev);
+  cudaFree(h->ulv_pool_dev);
   cudaFree(h->tasks_dev);
   cudaFree(h->z_dev);
   cudaFree(h->f_dev);
@@ -1280,9 +1291,18 @@ static int select_adjoint(hssb_matrix* h) {
   return tw;
 }
 
+// Mode 2 (hssb_solve): the factor pool must exist; the first solve factorises.
+static int prepare_solve(hssb_matrix* h) {
+  if (h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
+  if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle: hssb200 has no CPU fallback, the solve needs a B200");
+  if (!h->ulv_factored || !h->ulv_pool_dev) return ulv_factor_device(h);
+  return HSSB_OK;
+}
+
 static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* dX, int64_t ldx,
                            double* dY, int64_t ldy, double alpha, double beta, void* stream) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
+  if (trans == 2 && h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
   // DimensionMismatch checks of matmul.jl:19-20 (for A' the roles of the two dimensions swap)
   const int64_t need_x = trans ? h->local_m : h->local_n, need_y = trans ? h->local_n : h->local_m;
   if (rows_x != need_x)
@@ -1298,13 +1318,17 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
   if ((rows_x > 0 && !dX) || !dY) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL matrix pointer");
   DeviceGuard dg(h->device);
   if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
-  int rc = ensure_workspace(h, nrhs);
+  int rc = ensure_workspace(h, nrhs, trans == 2);
   if (rc) return rc;
   const double* pool = h->pool_dev;
-  if (trans) {
+  if (trans == 1) {
     rc = select_adjoint(h);
     if (rc < 0) return rc;
     if (rc == 0) { pool = h->pool_t_dev; trans = 0; }  // A' X = the forward plan over the twin pool
+  } else if (trans == 2) {
+    rc = prepare_solve(h);
+    if (rc) return rc;
+    pool = h->ulv_pool_dev;
   }
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   CallParams cp;
@@ -1319,6 +1343,7 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
 static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx,
                             double* Y, int64_t ldy, double alpha, double beta) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
+  if (trans == 2 && h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
   const int64_t need_x = trans ? h->local_m : h->local_n, need_y = trans ? h->local_n : h->local_m;
   if (rows_x != need_x)
     HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: first dimension of B (%lld) does not match second dimension of A (%lld)",
@@ -1333,9 +1358,12 @@ static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t r
   if ((rows_x > 0 && !X) || !Y) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL matrix pointer");
   DeviceGuard dg(h->device);
   if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
-  if (trans) {  // fail before any copy is queued
+  if (trans == 1) {  // fail before any copy is queued
     const int a = select_adjoint(h);
     if (a < 0) return a;
+  } else if (trans == 2) {
+    const int a = prepare_solve(h);
+    if (a) return a;
   }
   if (nrhs > h->stage_nrhs) {
     cudaFree(h->x_stage); cudaFree(h->y_stage);
@@ -1418,6 +1446,39 @@ int hssb_matmul_t(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, 
 int hssb_matmul_t_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* dX, int64_t ldx, double* dY,
                       int64_t ldy, double alpha, double beta, void* stream) {
   return matmul_dev_impl(h, 1, rows_y, rows_x, nrhs, dX, ldx, dY, ldy, alpha, beta, stream);
+}
+
+// hssA \ B (hssmatrix.jl:234 -> ulvfactsolve, ulvfactor.jl:10-19)
+int hssb_ulv_factor(hssb_matrix* h) {
+  if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_ulv_factor: NULL handle");
+  if (h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_ulv_factor: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
+  if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle: hssb200 has no CPU fallback, the factorisation needs a B200");
+  DeviceGuard dg(h->device);
+  if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
+  invalidate_graphs(h);
+  return ulv_factor_device(h);
+}
+
+int hssb_solve(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* B, int64_t ldb, double* Z, int64_t ldz) {
+  return matmul_host_impl(h, 2, rows, rows, nrhs, B, ldb, Z, ldz, 1.0, 0.0);
+}
+
+int hssb_solve_dev(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* dB, int64_t ldb, double* dZ, int64_t ldz,
+                   void* stream) {
+  return matmul_dev_impl(h, 2, rows, rows, nrhs, dB, ldb, dZ, ldz, 1.0, 0.0, stream);
+}
+
+int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* o) {
+  if (!h || !o) HSSB_FAIL(HSSB_ERR_ARG, "hssb_ulv_info: NULL argument");
+  memset(o, 0, sizeof(*o));
+  o->supported = h->ulv.empty() ? 0 : 1;
+  o->factored = h->ulv_factored ? 1 : 0;
+  if (!h->ulv.empty()) {
+    o->pool_bytes = h->ulv_pool_len * 8;
+    o->flops_per_rhs = h->ulv_flops_per_rhs;
+    o->z_rows = h->ulv_z_rows; o->f_rows = h->ulv_f_rows;
+  }
+  return HSSB_OK;
 }
 
 int hssb_sync(hssb_matrix* h) {
@@ -1695,7 +1756,7 @@ int hssb_plan_only_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t
 int hssb_debug_counts(const hssb_matrix* h, int64_t* n_tasks, int64_t* n_phases, int64_t* pool_len) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_counts: NULL handle");
   if (n_tasks) *n_tasks = (int64_t)h->tasks_host.size();
-  if (n_phases) *n_phases = (int64_t)h->phases.size() + (int64_t)h->phases_t.size();  // transposed plan follows
+  if (n_phases) *n_phases = (int64_t)(h->phases.size() + h->phases_t.size() + h->phases_u.size());  // forward, transposed, ULV solve
   if (pool_len) *pool_len = h->pool_len;
   return HSSB_OK;
 }
@@ -1711,11 +1772,13 @@ int hssb_debug_task(const hssb_matrix* h, int64_t i, hssb_task_t* o) {
 }
 
 int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* o) {
-  if (!h || !o || i < 0 || i >= (int64_t)(h->phases.size() + h->phases_t.size())) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_phase: bad argument");
-  const bool tr = i >= (int64_t)h->phases.size();
-  const Phase& p = tr ? h->phases_t[(size_t)i - h->phases.size()] : h->phases[(size_t)i];
+  if (!h || !o || i < 0 || i >= (int64_t)(h->phases.size() + h->phases_t.size() + h->phases_u.size()))
+    HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_phase: bad argument");
+  const size_t nf = h->phases.size(), nt = h->phases_t.size();
+  const int which = (size_t)i < nf ? 0 : (size_t)i < nf + nt ? 1 : 2;
+  const Phase& p = which == 0 ? h->phases[(size_t)i] : which == 1 ? h->phases_t[(size_t)i - nf] : h->phases_u[(size_t)i - nf - nt];
   o->kind = p.kind; o->task0 = p.task0; o->ntasks = p.ntasks; o->maxM = p.maxM; o->level = p.level;
-  o->top = p.top; o->fast = p.fast; o->transposed = tr;
+  o->top = p.top; o->fast = p.fast; o->transposed = which;
   o->xchg_zoff = h->xchg_zoff; o->xchg_slot_rows = h->xchg_slot_rows;
   return HSSB_OK;
 }
@@ -1747,6 +1810,27 @@ int hssb_debug_pool_t(const hssb_matrix* h, double* out, int64_t len) {
   for (const TwinBlock& b : tb)
     for (int64_t c = 0; c < b.cols; ++c)
       for (int64_t r = 0; r < b.rows; ++r) out[b.dst + r * b.ld_dst + c] = h->pool_host[(size_t)(b.src + c * b.ld_src + r)];
+  return HSSB_OK;
+}
+
+// ULV test hooks: factorise a plan-only handle on the HOST with the same node routine the device
+// kernel runs (single-thread team), and expose the factor pool so that the numpy plan interpreter can
+// run the solve's task table (phases with transposed == 2) over it.
+int hssb_debug_ulv_factor_host(hssb_matrix* h) {
+  if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_ulv_factor_host: NULL handle");
+  if (h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_ulv_factor_host: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
+  if (h->pool_host.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_ulv_factor_host: plan-only handles only");
+  ulv_factor_host(h);
+  return HSSB_OK;
+}
+
+int hssb_debug_ulv_pool(const hssb_matrix* h, double* out, int64_t len) {
+  if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_ulv_pool: NULL handle");
+  if (h->ulv.empty() || !h->ulv_factored) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_ulv_pool: not factorised");
+  if (!out || len < h->ulv_pool_len) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_ulv_pool: need %lld doubles", (long long)h->ulv_pool_len);
+  if (!h->ulv_pool_host.empty()) { memcpy(out, h->ulv_pool_host.data(), (size_t)h->ulv_pool_len * 8); return HSSB_OK; }
+  DeviceGuard dg(h->device);
+  HSSB_CUDA(cudaMemcpy(out, h->ulv_pool_dev, (size_t)h->ulv_pool_len * 8, cudaMemcpyDeviceToHost));
   return HSSB_OK;
 }
 

@@ -61,7 +61,7 @@ struct CallParams {
   int64_t ldx, ldy;
   int32_t nrhs;
   double alpha, beta;
-  int32_t trans;  // 1: Y = A' X (transposed plan)
+  int32_t trans;  // 0: Y = A X, 1: Y = A' X (transposed task table), 2: ULV solve Y = A \ X (phases_u over the factor pool)
   int32_t debug;  // HSSB_OPT_DEBUG bits: 1 = leaf kernels compute without waiting for data, 2 = move data without computing
 };
 
@@ -94,6 +94,34 @@ struct TwinBlock {
   int32_t rows, cols, ld_src, ld_dst;
 };
 
+// ULV solver (src/ulvfactor.jl): shapes and offsets of one node of the implicit factorisation.
+// "Incoming" = the reduced problem that reaches the node: the leaf's own D/U/V, or the merge of
+// the two children's reduced blocks (ulvfactor.jl:74-79).
+struct UlvNode {
+  int32_t m_in = 0, n_in = 0;   // rows / columns of the incoming diagonal block
+  int32_t kr = 0, kw = 0;       // generator ranks (columns of U / V)
+  int32_t k = 0;                // rows handed to the parent: kr if compressible, else m_in
+  int32_t mk = 0;               // unknowns eliminated at this node (m_in - k, 0 if not compressible)
+  int32_t n_out = 0;            // columns handed to the parent (n_in - mk)
+  int32_t is_root = 0, is_leaf = 0;
+  int32_t left = -1, right = -1;
+  int32_t k1 = 0, kr1 = 0, kw1 = 0, no1 = 0, k2 = 0, kr2 = 0, kw2 = 0, no2 = 0;  // children
+  // primary pool blocks (pool offsets / leading dimensions; V and W are stored transposed)
+  int64_t D = -1, U = -1, V = -1, B12 = -1, B21 = -1, R1 = -1, R2 = -1, W1 = -1, W2 = -1;
+  int32_t ldD = 0, ldU = 0, ldV = 0, ldB12 = 0, ldB21 = 0, ldR1 = 0, ldR2 = 0, ldW1 = 0, ldW2 = 0;
+  // factor pool blocks, column-major:
+  //   az[s]: mk rows, ac[s]: k + kw rows (root: n_in rows); leaf: one block of m_in columns (s = 0),
+  //   branch: one block per child s of k_s + kw_s columns.  pta: n_in x mk, ptb: n_in x n_out.
+  int64_t az[2] = {-1, -1}, ac[2] = {-1, -1}, pta = -1, ptb = -1;
+  int32_t ld_az = 2, ld_ac = 2, ld_pt = 2;
+  // reduced generators handed to the parent (scratch that lives during the factorisation only)
+  int64_t rD = -1, rU = -1, rV = -1;  // k x n_out, k x kr, n_out x kw (leading dimension = rows)
+  // solve workspaces (row offsets): Z space holds zloc (mk rows) and c = [b; u] (k + kw rows),
+  // F space holds t (the n_out trailing unknowns, written by the parent)
+  int64_t zloc = -1, c = -1, t = -1;
+  int32_t ld_zloc = 2, ld_c = 2, ld_t = 2;
+};
+
 enum PhaseKind : int { PH_LEAF_UP = 0, PH_MERGE, PH_EXCHANGE, PH_TRANSLATE, PH_LEAF_DOWN, PH_XCHG_ACK };
 
 struct Phase {
@@ -115,6 +143,16 @@ struct hssb_matrix {
   std::vector<int64_t> leaves;    // local leaves, left to right
   std::vector<hssb::Phase> phases;
   std::vector<hssb::Phase> phases_t;  // Y = A' X on the same generators (single shard)
+  // ULV solver (hssb_solve): plan built with the product plan, factor pool filled by hssb_ulv_factor
+  std::vector<hssb::Phase> phases_u;
+  std::vector<hssb::UlvNode> ulv;     // parallel to `nodes`; empty if the solver does not apply
+  std::string ulv_why;                // why it does not apply
+  int64_t ulv_pool_len = 0, ulv_red_len = 0, ulv_z_rows = 0, ulv_f_rows = 0;
+  int64_t ulv_flops_per_rhs = 0;
+  int32_t ulv_MI = 0, ulv_NI = 0, ulv_KR = 0, ulv_KW = 0;  // scratch maxima
+  double* ulv_pool_dev = nullptr;
+  std::vector<double> ulv_pool_host;  // plan-only handles: factorised on the host by the test hook
+  bool ulv_factored = false;
   std::vector<hssb::GTask> tasks_host;
   hssb::GTask* tasks_dev = nullptr;
   double* pool_dev = nullptr;
@@ -129,6 +167,7 @@ struct hssb_matrix {
   int64_t gen_elems = 0, flops_per_rhs = 0;
   int64_t z_rows = 0, f_rows = 0;
   int64_t ws_nrhs = 0;  // workspace capacity in columns
+  bool ws_ulv = false;  // workspaces sized for the ULV solve as well
   double* z_dev = nullptr;
   double* f_dev = nullptr;
   // staging for the host-pointer entry

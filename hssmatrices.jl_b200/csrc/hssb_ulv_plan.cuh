@@ -1,0 +1,286 @@
+// hssb_ulv_plan.cuh — host side of the ULV solver: shapes, factor-pool layout, the solve's task
+// table and the driver of the factorisation kernel.  Included by hssb_api.cu only (uses its
+// static helpers round_up / add_phase); the device code is hssb_ulv.cuh.
+#pragma once
+
+#include "hssb_ulv.cuh"
+
+namespace hssb {
+
+// Shapes of the implicit ULV factorisation depend on sizes and ranks only, so the whole solve plan is
+// built with the product plan; hssb_ulv_factor later fills the factor pool.
+static void build_plan_ulv(hssb_matrix* H) {
+  auto& nodes = H->nodes;
+  H->ulv.clear();
+  H->phases_u.clear();
+  auto unsupported = [&](const char* why) { H->ulv.clear(); H->ulv_why = why; };
+  if (H->n_shards != 1) return unsupported("the ULV solver runs on a single shard");
+  if (H->m != H->n || H->m == 0) return unsupported("the ULV solver needs a square matrix");
+  std::vector<UlvNode> uv(nodes.size());
+
+  // ---- shapes, children before parents (BFS order reversed)
+  for (size_t i = nodes.size(); i-- > 0;) {
+    const Node& t = nodes[i];
+    UlvNode& u = uv[i];
+    u.is_root = t.parent < 0;
+    u.is_leaf = t.leaf;
+    u.kr = (int32_t)t.kr; u.kw = (int32_t)t.kw;
+    if (t.leaf) {
+      u.m_in = (int32_t)t.m; u.n_in = (int32_t)t.n;
+      u.D = t.off[BK_D]; u.ldD = t.ld[BK_D];
+      u.U = t.off[BK_U]; u.ldU = t.ld[BK_U];
+      u.V = t.off[BK_V]; u.ldV = t.ld[BK_V];
+    } else {
+      const Node& l = nodes[(size_t)t.left];
+      const Node& r = nodes[(size_t)t.right];
+      const UlvNode& c1 = uv[(size_t)t.left];
+      const UlvNode& c2 = uv[(size_t)t.right];
+      u.left = (int32_t)t.left; u.right = (int32_t)t.right;
+      u.k1 = c1.k; u.kr1 = c1.kr; u.kw1 = c1.kw; u.no1 = c1.n_out;
+      u.k2 = c2.k; u.kr2 = c2.kr; u.kw2 = c2.kw; u.no2 = c2.n_out;
+      u.m_in = u.k1 + u.k2; u.n_in = u.no1 + u.no2;
+      u.B12 = t.off[BK_B12]; u.ldB12 = t.ld[BK_B12];
+      u.B21 = t.off[BK_B21]; u.ldB21 = t.ld[BK_B21];
+      u.R1 = l.off[BK_R]; u.ldR1 = l.ld[BK_R]; u.R2 = r.off[BK_R]; u.ldR2 = r.ld[BK_R];
+      u.W1 = l.off[BK_W]; u.ldW1 = l.ld[BK_W]; u.W2 = r.off[BK_W]; u.ldW2 = r.ld[BK_W];
+    }
+    if (u.is_root) {
+      if (u.m_in != u.n_in) return unsupported("the reduced root block of the ULV factorisation is not square");
+      u.k = 0; u.mk = 0; u.n_out = 0;
+    } else if (u.kr < u.m_in) {  // compressible (ulvfactor.jl:28-31)
+      u.k = u.kr; u.mk = u.m_in - u.kr;
+      if (u.mk > u.n_in) return unsupported("a node eliminates more rows than it has columns (ulvfactor.jl:29 nk < m-k)");
+      u.n_out = u.n_in - u.mk;
+    } else {                     // full-rank block, nothing is eliminated here (ulvfactor.jl:31-37)
+      u.k = u.m_in; u.mk = 0; u.n_out = u.n_in;
+    }
+  }
+
+  // ---- factor pool / reduced-generator scratch / workspaces
+  int64_t off = 0, red = 0, zo = 0, fo = 0;
+  auto place = [&](int64_t rows, int64_t cols, int32_t& ld) {
+    ld = (int32_t)std::max<int64_t>(round_up(rows, 2), 2);
+    if (rows == 0 || cols == 0) return (int64_t)-1;
+    const int64_t at = off;
+    off += round_up((int64_t)ld * cols, 16);
+    return at;
+  };
+  H->ulv_MI = H->ulv_NI = H->ulv_KR = H->ulv_KW = 1;
+  for (size_t i = 0; i < nodes.size(); ++i) {
+    UlvNode& u = uv[i];
+    H->ulv_MI = std::max(H->ulv_MI, u.m_in); H->ulv_NI = std::max(H->ulv_NI, u.n_in);
+    H->ulv_KR = std::max(H->ulv_KR, u.kr); H->ulv_KW = std::max(H->ulv_KW, u.kw);
+    const int64_t rows_c = u.is_root ? u.n_in : u.k + u.kw;
+    int32_t ld_tmp;
+    if (u.is_leaf) {
+      u.az[0] = place(u.mk, u.m_in, u.ld_az);
+      u.ac[0] = place(rows_c, u.m_in, u.ld_ac);
+    } else {
+      u.az[0] = place(u.mk, u.k1 + u.kw1, u.ld_az);
+      u.az[1] = place(u.mk, u.k2 + u.kw2, ld_tmp);
+      u.ac[0] = place(rows_c, u.k1 + u.kw1, u.ld_ac);
+      u.ac[1] = place(rows_c, u.k2 + u.kw2, ld_tmp);
+    }
+    if (!u.is_root) {
+      u.pta = place(u.n_in, u.mk, u.ld_pt);
+      u.ptb = place(u.n_in, u.n_out, ld_tmp);
+      u.rD = red; red += (int64_t)u.k * u.n_out;
+      u.rU = red; red += (int64_t)u.k * u.kr;
+      u.rV = red; red += (int64_t)u.n_out * u.kw;
+      u.ld_zloc = (int32_t)std::max<int64_t>(round_up(u.mk, 2), 2);
+      u.ld_c = (int32_t)std::max<int64_t>(round_up(u.k + u.kw, 2), 2);
+      u.ld_t = (int32_t)std::max<int64_t>(round_up(u.n_out, 2), 2);
+      u.zloc = zo; zo += u.ld_zloc;
+      u.c = zo; zo += u.ld_c;
+      u.t = fo; fo += u.ld_t;
+    }
+  }
+  H->ulv_pool_len = std::max<int64_t>(off, 16);
+  H->ulv_red_len = std::max<int64_t>(red, 16);
+  H->ulv_z_rows = std::max<int64_t>(zo, 2);
+  H->ulv_f_rows = std::max<int64_t>(fo, 2);
+
+  // ---- the solve's task table: C = A0*B0 + A1*B1 over the factor pool
+  std::vector<GTask> batch;
+  auto& out = H->phases_u;
+  int64_t flops = 0;
+  auto blank = []() { GTask g; memset(&g, 0, sizeof(g)); g.lda0 = g.lda1 = g.ldb0 = g.ldb1 = g.ldc = 2; g.a0 = g.a1 = -1; return g; };
+  auto push = [&](GTask g) {
+    if (g.a0 < 0) g.K0 = 0;
+    if (g.a1 < 0) g.K1 = 0;
+    if (g.M <= 0) return;
+    flops += 2ll * g.M * ((int64_t)g.K0 + g.K1);
+    batch.push_back(g);
+  };
+  // rows [r0, r0 + M) of the two-block operator [A(:, child 1 columns) | A(:, child 2 columns)] applied to (c1, c2)
+  auto merge_rows = [&](const UlvNode& u, const int64_t a[2], int32_t lda, int64_t r0, int32_t M) {
+    const UlvNode& c1 = uv[(size_t)u.left];
+    const UlvNode& c2 = uv[(size_t)u.right];
+    GTask g = blank();
+    g.M = M;
+    if (a[0] >= 0) { g.a0 = a[0] + r0; g.lda0 = lda; g.sb0 = SRC_Z; g.b0 = c1.c; g.ldb0 = c1.ld_c; g.K0 = c1.k + c1.kw; }
+    if (a[1] >= 0) { g.a1 = a[1] + r0; g.lda1 = lda; g.sb1 = SRC_Z; g.b1 = c2.c; g.ldb1 = c2.ld_c; g.K1 = c2.k + c2.kw; }
+    return g;
+  };
+
+  if (uv[0].is_leaf) {  // hssA.D \ b (ulvfactor.jl:11-12)
+    const UlvNode& u = uv[0];
+    GTask g = blank();
+    g.a0 = u.ac[0]; g.lda0 = u.ld_ac; g.sb0 = SRC_X; g.b0 = 0; g.K0 = u.m_in; g.M = u.n_in;
+    g.sc = SRC_Y; g.c = 0;
+    push(g);
+    add_phase(H, PH_LEAF_DOWN, 0, false, batch, &out);
+  } else {
+    // upsweep, leaves: zloc = T1 b, c = [T2; T3] b
+    for (int64_t li : H->leaves) {
+      const UlvNode& u = uv[(size_t)li];
+      const Node& t = nodes[(size_t)li];
+      for (int part = 0; part < 2; ++part) {
+        GTask g = blank();
+        g.a0 = part ? u.ac[0] : u.az[0]; g.lda0 = part ? u.ld_ac : u.ld_az;
+        g.sb0 = SRC_X; g.b0 = t.row0; g.K0 = u.m_in;
+        g.M = part ? u.k + u.kw : u.mk;
+        g.sc = SRC_Z; g.c = part ? u.c : u.zloc; g.ldc = part ? u.ld_c : u.ld_zloc;
+        push(g);
+      }
+    }
+    add_phase(H, PH_LEAF_UP, 0, false, batch, &out);
+    // upsweep, branches by height
+    for (int h = 1; h < nodes[0].height; ++h) {
+      for (size_t i = 0; i < nodes.size(); ++i) {
+        const Node& t = nodes[i];
+        if (t.leaf || t.height != h || t.parent < 0) continue;
+        const UlvNode& u = uv[i];
+        GTask g = merge_rows(u, u.az, u.ld_az, 0, u.mk);
+        g.sc = SRC_Z; g.c = u.zloc; g.ldc = u.ld_zloc;
+        push(g);
+        g = merge_rows(u, u.ac, u.ld_ac, 0, u.k + u.kw);
+        g.sc = SRC_Z; g.c = u.c; g.ldc = u.ld_c;
+        push(g);
+      }
+      add_phase(H, PH_MERGE, h, false, batch, &out);
+    }
+    // root: [t1; t2] = D^-1 b (ulvfactor.jl:83), rows split between the children
+    {
+      const UlvNode& u = uv[0];
+      const UlvNode& c1 = uv[(size_t)u.left];
+      const UlvNode& c2 = uv[(size_t)u.right];
+      GTask g = merge_rows(u, u.ac, u.ld_ac, 0, u.no1);
+      g.sc = SRC_F; g.c = c1.t; g.ldc = c1.ld_t;
+      push(g);
+      g = merge_rows(u, u.ac, u.ld_ac, u.no1, u.no2);
+      g.sc = SRC_F; g.c = c2.t; g.ldc = c2.ld_t;
+      push(g);
+      add_phase(H, PH_TRANSLATE, 0, false, batch, &out);
+    }
+    // top-down: z[cols] = P' [zloc; t] (ulvfactor.jl:98-107); a branch hands the result to its children
+    auto down = [&](const UlvNode& u, int64_t r0, int32_t M) {
+      GTask g = blank();
+      g.M = M;
+      if (u.pta >= 0) { g.a0 = u.pta + r0; g.lda0 = u.ld_pt; g.sb0 = SRC_Z; g.b0 = u.zloc; g.ldb0 = u.ld_zloc; g.K0 = u.mk; }
+      if (u.ptb >= 0) { g.a1 = u.ptb + r0; g.lda1 = u.ld_pt; g.sb1 = SRC_F; g.b1 = u.t; g.ldb1 = u.ld_t; g.K1 = u.n_out; }
+      return g;
+    };
+    for (int d = 1; d <= (int)H->depth; ++d) {
+      for (size_t i = 0; i < nodes.size(); ++i) {
+        const Node& t = nodes[i];
+        if (t.leaf || t.depth != d) continue;
+        const UlvNode& u = uv[i];
+        const UlvNode& c1 = uv[(size_t)u.left];
+        const UlvNode& c2 = uv[(size_t)u.right];
+        GTask g = down(u, 0, u.no1);
+        g.sc = SRC_F; g.c = c1.t; g.ldc = c1.ld_t;
+        push(g);
+        g = down(u, u.no1, u.no2);
+        g.sc = SRC_F; g.c = c2.t; g.ldc = c2.ld_t;
+        push(g);
+      }
+      add_phase(H, PH_TRANSLATE, d, false, batch, &out);
+    }
+    for (int64_t li : H->leaves) {
+      const UlvNode& u = uv[(size_t)li];
+      GTask g = down(u, 0, u.n_in);
+      g.sc = SRC_Y; g.c = nodes[(size_t)li].col0;
+      push(g);
+    }
+    add_phase(H, PH_LEAF_DOWN, 0, false, batch, &out);
+  }
+  H->ulv_flops_per_rhs = flops;
+  H->ulv = std::move(uv);
+  H->ulv_why.clear();
+}
+
+// Nodes grouped by height (children strictly below their parent).
+static std::vector<std::vector<int32_t>> ulv_levels(const hssb_matrix* H) {
+  std::vector<std::vector<int32_t>> lv((size_t)H->nodes[0].height + 1);
+  for (size_t i = 0; i < H->nodes.size(); ++i) lv[(size_t)H->nodes[i].height].push_back((int32_t)i);
+  return lv;
+}
+
+// Host instantiation of the factorisation (single-thread team) for plan-only handles: CPU tests only.
+static void ulv_factor_host(hssb_matrix* H) {
+  H->ulv_pool_host.assign((size_t)H->ulv_pool_len, 0.0);
+  std::vector<double> red((size_t)H->ulv_red_len, 0.0);
+  std::vector<double> scratch((size_t)ulv_scratch_len(H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW), 0.0);
+  UlvCtx cx{H->ulv.data(), H->pool_host.data(), H->ulv_pool_host.data(), red.data(), H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW};
+  const Team tm{0, 1};
+  for (auto& level : ulv_levels(H))
+    for (int32_t node : level) ulv_factor_node(tm, cx, node, scratch.data());
+  H->ulv_factored = true;
+}
+
+// Device factorisation: one launch per tree level, one CTA per node.
+static int ulv_factor_device(hssb_matrix* H) {
+  if (H->ulv_pool_dev) { cudaFree(H->ulv_pool_dev); H->ulv_pool_dev = nullptr; }
+  H->ulv_factored = false;
+  const size_t pool_b = (size_t)H->ulv_pool_len * sizeof(double);
+  if (cudaMalloc(&H->ulv_pool_dev, pool_b) != cudaSuccess) {
+    cudaGetLastError();
+    H->ulv_pool_dev = nullptr;
+    HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of the %.3f GB ULV factor pool failed", pool_b * 1e-9);
+  }
+  const auto levels = ulv_levels(H);
+  size_t widest = 1;
+  for (auto& l : levels) widest = std::max(widest, l.size());
+  const int64_t stride = round_up(ulv_scratch_len(H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW), 16);
+  // CTAs in flight: two per SM, fewer when the scratch of large nodes would not fit in 8 GiB
+  int ctas = (int)std::min<size_t>(widest, 148 * 2);
+  while (ctas > 1 && (size_t)ctas * (size_t)stride * 8 > ((size_t)8 << 30)) ctas /= 2;
+  UlvNode* d_nodes = nullptr;
+  int32_t* d_list = nullptr;
+  double *d_red = nullptr, *d_scratch = nullptr;
+  auto cleanup = [&]() { cudaFree(d_nodes); cudaFree(d_list); cudaFree(d_red); cudaFree(d_scratch); };
+  cudaError_t e = cudaMalloc(&d_nodes, H->ulv.size() * sizeof(UlvNode));
+  if (e == cudaSuccess) e = cudaMalloc(&d_list, H->nodes.size() * sizeof(int32_t));
+  if (e == cudaSuccess) e = cudaMalloc(&d_red, (size_t)H->ulv_red_len * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_scratch, (size_t)ctas * (size_t)stride * sizeof(double));
+  if (e == cudaSuccess) e = cudaMemsetAsync(H->ulv_pool_dev, 0, pool_b, H->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_nodes, H->ulv.data(), H->ulv.size() * sizeof(UlvNode), cudaMemcpyHostToDevice, H->stream);
+  std::vector<int32_t> flat;
+  for (auto& l : levels) flat.insert(flat.end(), l.begin(), l.end());
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_list, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, H->stream);
+  if (e == cudaSuccess) {
+    UlvCtx cx{d_nodes, H->pool_dev, H->ulv_pool_dev, d_red, H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW};
+    size_t at = 0;
+    for (auto& l : levels) {
+      if (!l.empty()) {
+        const int grid = (int)std::min<size_t>(l.size(), (size_t)ctas);
+        ulv_factor_kernel<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, stride);
+        H->launches++;
+      }
+      at += l.size();
+    }
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(H->stream);
+  cleanup();
+  if (e != cudaSuccess) {
+    cudaFree(H->ulv_pool_dev);
+    H->ulv_pool_dev = nullptr;
+    HSSB_FAIL(HSSB_ERR_CUDA, "ULV factorisation failed: %s", cudaGetErrorString(e));
+  }
+  H->ulv_factored = true;
+  return HSSB_OK;
+}
+
+}  // namespace hssb

@@ -171,6 +171,27 @@ int hssb_matmul_t_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nr
                       void* stream);
 int hssb_sync(hssb_matrix* h);
 
+/* ---- the solver: hssA \ B --------------------------------------------- */
+/* `\(hssA::HssMatrix, B::Matrix)` (hssmatrix.jl:234) = ulvfactsolve (ulvfactor.jl:10-19): implicit
+ * ULV factorisation (Chandrasekaran, Gu, Pals 2006).  The reference factorises and solves in one
+ * recursive pass on EVERY call; here hssb_ulv_factor runs the factorisation once on the device
+ * (Householder QR / LQ per node, level by level, folded into explicit per-node matrices in a second
+ * level-ordered pool) and hssb_solve applies it to any number of right-hand sides with the level
+ * schedule and kernels of the product.  Square matrices, single shard.  hssb_solve factorises on
+ * first use; call hssb_ulv_factor to do it ahead of time.  B is rows x nrhs, Z (the solution) too.  */
+int hssb_ulv_factor(hssb_matrix* h);
+int hssb_solve(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* B, int64_t ldb, double* Z, int64_t ldz);
+int hssb_solve_dev(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* dB, int64_t ldb, double* dZ,
+                   int64_t ldz, void* stream);
+typedef struct hssb_ulv_info_t {
+  int64_t supported;     /* 1 if hssb_solve applies to this handle                              */
+  int64_t factored;      /* 1 once the factor pool exists                                       */
+  int64_t pool_bytes;    /* device bytes of the factor pool                                     */
+  int64_t flops_per_rhs; /* flops of one solve per right-hand-side column (factors x 8 B = bytes read / 2) */
+  int64_t z_rows, f_rows; /* workspace rows of the solve                                        */
+} hssb_ulv_info_t;
+int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
+
 /* Options. */
 #define HSSB_OPT_FORCE_GENERIC 1 /* 1: never use the fixed-shape DMMA kernels (debug/parity)  */
 #define HSSB_OPT_USE_GRAPH 2     /* 1: replay the level schedule as a CUDA graph              */
@@ -236,7 +257,7 @@ typedef struct hssb_phase_t {
   int64_t kind; /* 0 leaf-up, 1 merge, 2 exchange, 3 translate, 4 leaf-down */
   int64_t task0, ntasks, maxM, level, top, fast;
   int64_t xchg_zoff, xchg_slot_rows;
-  int64_t transposed; /* 1: belongs to the plan of hssb_matmul_t (listed after the forward plan) */
+  int64_t transposed; /* 0: forward plan, 1: plan of hssb_matmul_t, 2: plan of hssb_solve over the ULV factor pool */
 } hssb_phase_t;
 int hssb_plan_only(hssb_builder* b, int64_t root, int shard_rank, int n_shards, hssb_matrix** out);
 int hssb_plan_only_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, int shard_rank,
@@ -246,6 +267,10 @@ int hssb_debug_task(const hssb_matrix* h, int64_t i, hssb_task_t* out);
 int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* out);
 int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len);
 int hssb_debug_pool_t(const hssb_matrix* h, double* out, int64_t len); /* image of the adjoint twin pool */
+/* ULV: factorise a plan-only handle on the host with the device's node routine (single-thread team),
+ * and read the factor pool (either kind of handle) for the numpy plan interpreter.                   */
+int hssb_debug_ulv_factor_host(hssb_matrix* h);
+int hssb_debug_ulv_pool(const hssb_matrix* h, double* out, int64_t len);
 
 #ifdef __cplusplus
 }

@@ -28,3 +28,9 @@ def hb():
 def oracle():
     import hss_oracle
     return hss_oracle
+
+
+@pytest.fixture(scope="session")
+def ulv_oracle():
+    import hss_ulv_oracle
+    return hss_ulv_oracle

@@ -13,15 +13,15 @@ class ShardState:
     def __init__(self, packed, X, Y, nrhs, pool=None):
         self.packed = packed
         self.tasks, self.phases, self.pool = packed.debug_plan()
-        if pool is not None:  # e.g. the adjoint twin pool: same layout, same plan
-            assert pool.shape == self.pool.shape
+        if pool is not None:  # the adjoint twin pool (same layout, same plan) or the ULV factor pool
             self.pool = pool
         self.nrhs = nrhs
         self.X = np.asfortranarray(X)
         self.Y = Y
         # poison the workspaces: reading an unwritten block must show up as NaN
-        self.Z = np.full(packed.info.z_rows * nrhs, np.nan)
-        self.F = np.full(packed.info.f_rows * nrhs, np.nan)
+        ui = packed.ulv_info   # the ULV solve uses more workspace rows per node than the product
+        self.Z = np.full(max(packed.info.z_rows, ui.z_rows) * nrhs, np.nan)
+        self.F = np.full(max(packed.info.f_rows, ui.f_rows) * nrhs, np.nan)
 
     def _a(self, off, ld, rows, cols, trans):
         if rows == 0 or cols == 0:
@@ -65,8 +65,9 @@ class ShardState:
 def run_plan(packed, X, Y, alpha=1.0, beta=0.0, trans=False, pool=None):
     """Single-shard plan: Y (in place) = alpha*op(A)*X + beta*Y, op(A) = A' if trans."""
     st = ShardState(packed, X, Y, X.shape[1], pool)
+    mode = int(trans)   # 0 forward, 1 transposed task table, 2 ULV solve (pool = the factor pool)
     for ph in st.phases:
-        if bool(ph.transposed) != bool(trans):
+        if ph.transposed != mode:
             continue
         assert ph.kind != PH_EXCHANGE
         st.run_phase(ph, alpha, beta)
