@@ -13,8 +13,9 @@ module HssMatricesB200
 using HssMatrices
 using HssMatrices: HssMatrix, isleaf, gensize
 using LinearAlgebra
-import Base: *
+import Base: *, \
 import LinearAlgebra: mul!
+import HssMatrices: ulvfactsolve
 
 const libhssb = get(ENV, "HSSB200_LIB", joinpath(@__DIR__, "..", "lib", "libhssb200.so"))
 
@@ -134,6 +135,24 @@ function tmul!(C::StridedMatrix{Float64}, p::PackedHss, B::StridedMatrix{Float64
 end
 *(A::StridedMatrix{Float64}, p::PackedHss) = copy(tmul!(Matrix{Float64}(undef, size(p, 2), size(A, 1)), p, copy(A'), 1.0, 0.0)')
 
+# hssA \ B (src/hssmatrix.jl:234) = ulvfactsolve (src/ulvfactor.jl:10-19).  The reference factorises and
+# solves in one pass on every call; the library factorises once per packed handle (hssb_ulv_factor, on
+# the device) and every further solve only applies the stored factors.
+function ulvfactsolve(p::PackedHss, B::StridedMatrix{Float64})
+  size(p, 1) == size(B, 1) || throw(DimensionMismatch("First dimension of B does not match first dimension of A."))
+  stride(B, 1) == 1 || throw(ArgumentError("B needs unit stride in the first dimension"))
+  Z = Matrix{Float64}(undef, size(p, 2), size(B, 2))
+  GC.@preserve B Z begin
+    check(ccall((:hssb_solve, libhssb), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+      p.handle, size(B, 1), size(B, 2), pointer(B), max(stride(B, 2), 1), pointer(Z), max(size(Z, 1), 1)))
+  end
+  return Z
+end
+\(p::PackedHss, B::StridedMatrix{Float64}) = ulvfactsolve(p, B)
+\(p::PackedHss, b::StridedVector{Float64}) = reshape(ulvfactsolve(p, reshape(b, length(b), 1)), length(b))
+"""Factorise ahead of time (otherwise the first `\\` does it)."""
+ulvfactor!(p::PackedHss) = (check(ccall((:hssb_ulv_factor, libhssb), Cint, (Ptr{Cvoid},), p.handle)); p)
+
 # ---- drop-in methods on HssMatrix{Float64} ---------------------------------------------------
 # HssMatrix is mutable (recompress!, prune_leaves!, field assignment as in test/runtests.jl:75), so
 # the device copy is cached per object identity and must be dropped by hand after a mutation.
@@ -145,7 +164,9 @@ invalidate!(hssA::HssMatrix{Float64}) = (delete!(CACHE, hssA); nothing)
 mul!(C::StridedMatrix{Float64}, hssA::HssMatrix{Float64}, B::StridedMatrix{Float64}, α::Real, β::Real) = mul!(C, packed(hssA), B, α, β)
 *(hssA::HssMatrix{Float64}, B::StridedMatrix{Float64}) = packed(hssA) * B
 *(A::StridedMatrix{Float64}, hssB::HssMatrix{Float64}) = A * packed(hssB)
+\(hssA::HssMatrix{Float64}, B::Matrix{Float64}) = packed(hssA) \ B                      # src/hssmatrix.jl:234
+ulvfactsolve(hssA::HssMatrix{Float64}, B::Matrix{Float64}) = ulvfactsolve(packed(hssA), B)  # src/ulvfactor.jl:10
 
-export pack, PackedHss, invalidate!
+export pack, PackedHss, invalidate!, ulvfactor!
 
 end # module
