@@ -1,12 +1,14 @@
 // hssb_kernels_generic.cuh — any-shape tile kernel for one level of the HSS
-// product.  Handles ragged leaves (62/63 rows), variable and zero ranks,
-// unbalanced trees, nrhs not a multiple of anything.  One CTA = one 64x64 tile
-// of one task's output; K is walked in 16-wide slabs staged through shared
-// memory with coalesced (unit-stride) global reads for both A layouts; the next slab is
-// prefetched into registers while the current one is consumed.
+// product (and of the ULV solve).  Handles ragged leaves (62/63 rows), variable and
+// zero ranks, unbalanced trees, nrhs not a multiple of anything.  One CTA = one 64x64
+// tile of one task's output; K is walked in 16-wide slabs staged through shared
+// memory with coalesced (unit-stride) global reads for both A layouts (masked, zero
+// filled); the next slab is prefetched into registers while the current one is
+// consumed with FP64 tensor-core DMMA m8n8k4 from conflict-free shared-memory images.
 #pragma once
 
 #include "hssb_internal.h"
+#include "hssb_mma.cuh"
 
 namespace hssb {
 
@@ -22,7 +24,17 @@ __device__ __forceinline__ const double* operand_b(const CallParams& p, int src,
   }
 }
 
-__global__ void __launch_bounds__(G_THREADS)
+// Shared-memory images of one K slab, laid out so that both the staging stores and the DMMA fragment
+// loads are bank-conflict free (16 doubles per bank row):
+//   A applied as stored ("N", column-major M x K): k-major  As[kk * G_SA + m],  G_SA = 68 = 4 mod 16
+//   A applied transposed (stored K x M):           m-major  As[m * G_SB + kk],  G_SB = 20 = 4 mod 16
+//   B (always read K-fastest from global):         n-major  Bs[n * G_SB + kk]
+// A fragment lane (g, t) reads A[m0 + g][k0 + t]: offsets 4t + g resp. 4g + t mod 16, all distinct
+// within a half warp.
+constexpr int G_SA = 68, G_SB = 20, G_SMEM = G_TM * G_SB;  // 1280 >= 16 * 68
+static_assert(G_TK * G_SA <= G_SMEM, "k-major image must fit");
+
+__global__ void __launch_bounds__(G_THREADS, 3)
 generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
   const GTask t = tasks[blockIdx.x];
   const int m0 = blockIdx.y * G_TM;
@@ -30,16 +42,20 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
   const int n0 = blockIdx.z * G_TN;
   const int N = p.nrhs;
 
-  __shared__ double As[G_TK][G_TM + 1];
-  __shared__ double Bs[G_TK][G_TN + 1];
+  __shared__ double As[G_SMEM];
+  __shared__ double Bs[G_SMEM];
 
   const int tid = threadIdx.x;
-  const int tx = tid & 15, ty = tid >> 4;
-  double acc[4][4];
+  // FP64 tensor path: 8 warps tile the 64 x 64 output as 2 (M) x 4 (N); a warp owns 32 x 16 =
+  // 4 x 2 m8n8 accumulators (DMMA m8n8k4), lane = 4 g + q.
+  const int lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+  double acc[4][2][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+    for (int j = 0; j < 2; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
   // The K loop runs over the slabs of both products back to back; the global loads of slab i+1
   // are issued into registers before slab i is consumed from shared memory, so a level of small
@@ -84,13 +100,13 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
     const bool ta = slab >= nslab0 ? t.ta1 : t.ta0;
     if (!ta) {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) As[(tid >> 6) + 4 * r][tid & 63] = ra[r];
+      for (int r = 0; r < 4; ++r) As[((tid >> 6) + 4 * r) * G_SA + (tid & 63)] = ra[r];
     } else {
 #pragma unroll
-      for (int r = 0; r < 4; ++r) As[tid & 15][(tid >> 4) + 16 * r] = ra[r];
+      for (int r = 0; r < 4; ++r) As[((tid >> 4) + 16 * r) * G_SB + (tid & 15)] = ra[r];
     }
 #pragma unroll
-    for (int r = 0; r < 4; ++r) Bs[tid & 15][(tid >> 4) + 16 * r] = rb[r];
+    for (int r = 0; r < 4; ++r) Bs[((tid >> 4) + 16 * r) * G_SB + (tid & 15)] = rb[r];
   };
 
   if (nslab > 0) fetch(0);
@@ -98,22 +114,26 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
     stage(slab);
     __syncthreads();
     if (slab + 1 < nslab) fetch(slab + 1);
+    const bool ta = slab >= nslab0 ? t.ta1 : t.ta0;
+    const double* ap = ta ? As + (wm + g) * G_SB + q : As + q * G_SA + wm + g;
+    const int a_tile = ta ? 8 * G_SB : 8, a_step = ta ? 4 : 4 * G_SA;  // next m8 tile / next k4 step
+    const double* bp = Bs + (wn + g) * G_SB + q;
 #pragma unroll
-    for (int kk = 0; kk < G_TK; ++kk) {
-      double a[4], b[4];
+    for (int ks = 0; ks < G_TK / 4; ++ks) {
+      double a[4], b[2];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][tx + 16 * i];
+      for (int i = 0; i < 4; ++i) a[i] = ap[ks * a_step + i * a_tile];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][ty + 16 * j];
+      for (int j = 0; j < 2; ++j) b[j] = bp[j * 8 * G_SB + ks * 4];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+        for (int j = 0; j < 2; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
     }
     __syncthreads();
   }
 
-  // ---- epilogue
+  // ---- epilogue: lane (g, q) of accumulator (i, j) holds C[wm + 8 i + g][wn + 8 j + 2 q + {0, 1}]
   int64_t ldc;
   double* C;
   switch (t.sc) {
@@ -122,22 +142,24 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
     default: ldc = p.ldy; C = p.Y + t.c; break;
   }
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {
-    const int col = n0 + ty + 16 * j;
-    if (col >= N) continue;
+  for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int row = m0 + tx + 16 * i;
-      if (row >= t.M) continue;
-      double* dst = C + (int64_t)col * ldc + row;
-      double v = acc[i][j];
-      if (t.epilogue) {
-        v *= p.alpha;
-        if (p.beta != 0.0) v += p.beta * (*dst);  // beta == 0 never reads Y (matmul.jl:13)
+    for (int e = 0; e < 2; ++e) {
+      const int col = n0 + wn + 8 * j + 2 * q + e;
+      if (col >= N) continue;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = m0 + wm + 8 * i + g;
+        if (row >= t.M) continue;
+        double* dst = C + (int64_t)col * ldc + row;
+        double v = acc[i][j][e];
+        if (t.epilogue) {
+          v *= p.alpha;
+          if (p.beta != 0.0) v += p.beta * (*dst);  // beta == 0 never reads Y (matmul.jl:13)
+        }
+        *dst = v;
       }
-      *dst = v;
     }
-  }
 }
 
 }  // namespace hssb
