@@ -956,11 +956,17 @@ static int launch_generic(hssb_matrix* H, const Phase& ph, const CallParams& cp,
   return HSSB_OK;
 }
 
+// 0: Y = A X, 1: Y = A' X (any-shape transposed task table), 2: ULV solve
+static const std::vector<Phase>& phase_list(const hssb_matrix* H, int mode) {
+  return mode == 2 ? H->phases_u : mode == 1 ? H->phases_t : H->phases;
+}
+
 static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
-  const std::vector<Phase>& phases = cp.trans == 2 ? H->phases_u : cp.trans ? H->phases_t : H->phases;
-  const bool prof = H->profile && !cp.trans;
+  const std::vector<Phase>& phases = phase_list(H, cp.trans);
+  const bool prof = H->profile;
   if (prof) {
-    while (H->prof_events.size() < H->phases.size() + 1) {
+    H->prof_mode = cp.trans;
+    while (H->prof_events.size() < phases.size() + 1) {
       cudaEvent_t e;
       HSSB_CUDA(cudaEventCreate(&e));
       H->prof_events.push_back(e);
@@ -1525,11 +1531,11 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
 
 int64_t hssb_launch_count(const hssb_matrix* h) { return h ? h->launches : 0; }
 
-int hssb_phase_count(const hssb_matrix* h) { return h ? (int)h->phases.size() : 0; }
+int hssb_phase_count(const hssb_matrix* h) { return h ? (int)phase_list(h, h->prof_mode).size() : 0; }
 
 int hssb_phase_time(hssb_matrix* h, int i, hssb_phase_time_t* o) {
-  if (!h || !o || i < 0 || i >= (int)h->phases.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_phase_time: bad argument");
-  const Phase& ph = h->phases[(size_t)i];
+  if (!h || !o || i < 0 || i >= (int)phase_list(h, h->prof_mode).size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_phase_time: bad argument");
+  const Phase& ph = phase_list(h, h->prof_mode)[(size_t)i];
   memset(o, 0, sizeof(*o));
   o->kind = ph.kind; o->level = ph.level; o->top = ph.top; o->fast = ph.fast; o->ntasks = ph.ntasks;
   int64_t gen = 0, xrows = 0, yrows = 0, fl = 0;

@@ -204,6 +204,7 @@ struct hssb_matrix {
   bool in_host_call = false;
   std::vector<cudaEvent_t> prof_events;  // HSSB_OPT_PROFILE: one event between consecutive phases
   int64_t prof_nrhs = 0;
+  int prof_mode = 0;  // which plan the last profiled call ran (0 product, 1 transposed task table, 2 ULV solve)
   // synthetic
   bool synthetic = false;
   uint64_t seed = 0;

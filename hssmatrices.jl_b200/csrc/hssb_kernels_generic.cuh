@@ -50,7 +50,11 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
   // 4 x 2 m8n8 accumulators (DMMA m8n8k4), lane = 4 g + q.
   const int lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
-  const int wm = (warp & 1) * 32, wn = (warp >> 1) * 16;
+  // Warps 0-3 (one per scheduler) own rows 0-31, warps 4-7 rows 32-63: when a task's last row tile
+  // holds 32 rows or fewer (M = 32, 96, ... are the common ranks) the upper warps skip the tensor
+  // work and every scheduler issues half as many DMMAs instead of two schedulers idling.
+  const int wm = (warp >> 2) * 32, wn = (warp & 3) * 16;
+  const bool active = m0 + wm < t.M && n0 + wn < N;
   double acc[4][2][2];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
@@ -118,6 +122,7 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
     const double* ap = ta ? As + (wm + g) * G_SB + q : As + q * G_SA + wm + g;
     const int a_tile = ta ? 8 * G_SB : 8, a_step = ta ? 4 : 4 * G_SA;  // next m8 tile / next k4 step
     const double* bp = Bs + (wn + g) * G_SB + q;
+    if (active) {
 #pragma unroll
     for (int ks = 0; ks < G_TK / 4; ++ks) {
       double a[4], b[2];
@@ -129,6 +134,7 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
       for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 2; ++j) mma_m8n8k4(acc[i][j][0], acc[i][j][1], a[i], b[j]);
+    }
     }
     __syncthreads();
   }

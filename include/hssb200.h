@@ -208,7 +208,9 @@ int64_t hssb_launch_count(const hssb_matrix* h);
 
 /* Per-phase accounting of the level schedule and, after a call made with
  * HSSB_OPT_PROFILE = 1 (graph replay off), its device time measured with CUDA
- * events on the launching stream.  kind: 0 leaf-up, 1 merge, 2 exchange,
+ * events on the launching stream.  The phases are those of the plan the last
+ * profiled call ran (product by default; hssb_matmul_t without the twin pool;
+ * hssb_solve).  kind: 0 leaf-up, 1 merge, 2 exchange,
  * 3 translate, 4 leaf-down.  ms < 0 if no profiled call was made.             */
 typedef struct hssb_phase_time_t {
   int64_t kind, level, top, fast, ntasks;

@@ -30,6 +30,19 @@ ms = e0.elapsed_time(e1) / 10
 fl = ui.flops_per_rhs * k
 by = ui.flops_per_rhs / 2 * 8 + 2 * 8 * n * k
 print(f"solve nrhs {k}: {ms:.3f} ms  {fl / ms * 1e-9:.2f} TFLOP/s  {by / ms * 1e-6:.0f} GB/s (factor matrices read once + B + Z)")
+# per-phase device times of the solve (plain launches + events)
+P.set_option(hb.OPT_USE_GRAPH, 0); P.set_option(hb.OPT_PROFILE, 1)
+acc = {}
+for it in range(4):
+    P.solve_dev(B.data_ptr(), n, Z.data_ptr(), n, k, stream=s.cuda_stream); torch.cuda.synchronize()
+    if it:
+        for ph in P.phase_times():
+            a = acc.setdefault(ph["name"], [0.0, ph["flops_per_rhs"] * k, ph["ntasks"]])
+            a[0] += ph["ms"] / 3
+big = {nm: v for nm, v in acc.items() if v[0] > 0.03 * ms}
+print("solve phases (ms, TFLOP/s, tasks):", {nm: (round(v[0], 3), round(v[1] / v[0] * 1e-9, 1), v[2]) for nm, v in big.items()},
+      "rest", round(sum(v[0] for nm, v in acc.items() if nm not in big), 3), "ms in", len(acc) - len(big), "phases")
+P.set_option(hb.OPT_PROFILE, 0); P.set_option(hb.OPT_USE_GRAPH, 1)
 # backward error: ||B - A Z|| / (||A||_2 ||Z||), ||A||_2 by power iteration with A and A'
 P.matmul_dev(Z.data_ptr(), n, Y.data_ptr(), n, k, stream=s.cuda_stream)
 torch.cuda.synchronize()
