@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", default="default", help="comma-separated switches: generic, nograph, nccl, adjoint (time Y = A' X)")
+    ap.add_argument("--variant", default="default", help="comma-separated switches: generic, nograph, nccl, adjoint (time Y = A' X), nosolve (skip the ULV solver extra)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = dict(CONFIGS[args.config])
@@ -305,6 +305,43 @@ def main():
                "d2h_bytes_per_step": 8 * rows * k, "ms_per_step": te.item() * 1e3, "steps": steps_e,
                "host_memory": "pinned", "matches_device_path": chk <= 1e-12}
 
+    # ---------------- the ULV solver on the same matrix (extra, config 3 only) -----
+    # Not part of `value`: SURVEY 8f rank 4 measured beside the product (factor once, then solves).
+    solve = None
+    if N == 1 and args.config == "c3" and not adjoint and "nosolve" not in variants:
+        try:
+            ui = P.ulv_info
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            P.ulv_factor()
+            torch.cuda.synchronize()
+            t_factor = time.perf_counter() - t0
+            Zs = torch.empty_like(X)
+            for _ in range(3):
+                P.solve_dev(X.data_ptr(), rows, Zs.data_ptr(), rows, k, stream=st)
+            steps_s = max(3, min(args.steps, 10))
+            s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s0.record()
+            for _ in range(steps_s):
+                P.solve_dev(X.data_ptr(), rows, Zs.data_ptr(), rows, k, stream=st)
+            s1.record()
+            torch.cuda.synchronize()
+            ms_solve = s0.elapsed_time(s1) / steps_s
+            P.matmul_dev(Zs.data_ptr(), rows, Y.data_ptr(), rows, k, 1.0, 0.0, stream=st)   # A (A \ X) - X
+            torch.cuda.synchronize()
+            resid = float(torch.linalg.norm(Y - X) / torch.linalg.norm(X))
+            fl_s = ui.flops_per_rhs * k
+            by_s = ui.flops_per_rhs // 2 * 8 + 2 * 8 * rows * k
+            solve = {"what": "Z = A \\ X (hssb_solve_dev, ULV factors resident, device time per call)", "ms_per_solve": ms_solve,
+                     "gflops": fl_s / ms_solve * 1e-6, "flops": fl_s, "algorithmic_bytes": by_s, "hbm_gbs": by_s / ms_solve * 1e-6,
+                     "factor_ms_once": t_factor * 1e3, "factor_pool_gb": ui.pool_bytes * 1e-9,
+                     "relative_residual": resid, "steps": steps_s,
+                     "note": "||A Z - X|| / ||X|| with A Z from the product path; the synthetic matrix is ill conditioned "
+                             "(cond ~ 1e7), the scale-free backward error ||A Z - X|| / (||A||_2 ||Z||) is asserted <= 1e-12 in "
+                             "tests/test_gpu_ulv.py (measured 6e-17)"}
+        except hb.HssbError as e:
+            solve = {"error": str(e)}
+
     # ---------------- measured peaks + roofline --------------------------------
     out = None
     if rank == 0:
@@ -357,6 +394,7 @@ def main():
             "gpu_launches": int(launches_all),
             "clocks": clocks,
             "e2e": e2e,
+            "ulv_solve": solve,
         }
     # ---------------- CPU baseline (rank 0, N = 1 only) -------------------------
     if rank == 0 and N == 1 and not args.no_cpu:
