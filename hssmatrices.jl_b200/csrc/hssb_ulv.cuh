@@ -64,21 +64,33 @@ HSSB_HD Mat colmajor(const double* p, int64_t ld) { return Mat{const_cast<double
 
 // C (M x N) = alpha * A (M x K) * B (K x N) + beta * C   (beta == 0 never reads C)
 HSSB_HD void tm_gemm(const Team& tm, Mat C, Mat A, Mat B, int M, int N, int K, double alpha, double beta) {
+  // C never overlaps A or B (callers pass distinct blocks): without __restrict__ every store to C
+  // would order the following loads behind it
   const int64_t total = (int64_t)M * N;
   for (int64_t e = tm.tid; e < total; e += tm.nt) {
     const int i = (int)(e % M), j = (int)(e / M);
-    double s = 0.0;
-    for (int kk = 0; kk < K; ++kk) s = fma(A(i, kk), B(kk, j), s);
-    C(i, j) = beta == 0.0 ? alpha * s : alpha * s + beta * C(i, j);
+    const double* __restrict__ a = A.p + i * A.rs;
+    const double* __restrict__ b = B.p + j * B.cs;
+    double s0 = 0.0, s1 = 0.0;
+    int kk = 0;
+    for (; kk + 1 < K; kk += 2) {  // two independent accumulation chains
+      s0 = fma(a[kk * A.cs], b[kk * B.rs], s0);
+      s1 = fma(a[(kk + 1) * A.cs], b[(kk + 1) * B.rs], s1);
+    }
+    if (kk < K) s0 = fma(a[kk * A.cs], b[kk * B.rs], s0);
+    const double sum = s0 + s1;
+    C(i, j) = beta == 0.0 ? alpha * sum : alpha * sum + beta * C(i, j);
   }
   tm.sync();
 }
 
 HSSB_HD void tm_copy(const Team& tm, Mat dst, Mat src, int M, int N, double scale = 1.0) {
   const int64_t total = (int64_t)M * N;
+  double* __restrict__ d = dst.p;  // dst and src never overlap
+  const double* __restrict__ sp = src.p;
   for (int64_t e = tm.tid; e < total; e += tm.nt) {
     const int i = (int)(e % M), j = (int)(e / M);
-    dst(i, j) = scale * src(i, j);
+    d[i * dst.rs + j * dst.cs] = scale * sp[i * src.rs + j * src.cs];
   }
   tm.sync();
 }
@@ -87,7 +99,7 @@ HSSB_HD void tm_add(const Team& tm, Mat dst, Mat src, int M, int N) {
   const int64_t total = (int64_t)M * N;
   for (int64_t e = tm.tid; e < total; e += tm.nt) {
     const int i = (int)(e % M), j = (int)(e / M);
-    dst(i, j) += src(i, j);
+    dst(i, j) += src(i, j);  // tiny blocks (kw x kw_s), no need to untangle the aliasing
   }
   tm.sync();
 }
@@ -119,13 +131,24 @@ HSSB_HD void tm_qr(const Team& tm, Mat A, int p, int q, Mat Qt, int nq) {
     const double beta = act ? 2.0 / (tail + v0 * v0) : 0.0;
     if (act) {
       const int na = q - j - 1, ncol = na + nq;
+      // column j (the reflector) is only read during this step and never overlaps the column a
+      // thread updates: __restrict__ lets the loads run ahead of the stores
+      const double* __restrict__ v = A.p + j * A.cs;
+      const int64_t vs = A.rs;
       for (int cc = tm.tid; cc < ncol; cc += tm.nt) {
         const Mat Mx = cc < na ? A.sub(0, j + 1 + cc) : Qt.sub(0, cc - na);
-        double w = v0 * Mx(j, 0);
-        for (int i = j + 1; i < p; ++i) w = fma(A(i, j), Mx(i, 0), w);
-        w *= beta;
-        Mx(j, 0) -= w * v0;
-        for (int i = j + 1; i < p; ++i) Mx(i, 0) = fma(-w, A(i, j), Mx(i, 0));
+        double* __restrict__ x = Mx.p;
+        const int64_t xs = Mx.rs;
+        double w0 = v0 * x[j * xs], w1 = 0.0;
+        int i = j + 1;
+        for (; i + 1 < p; i += 2) {
+          w0 = fma(v[i * vs], x[i * xs], w0);
+          w1 = fma(v[(i + 1) * vs], x[(i + 1) * xs], w1);
+        }
+        if (i < p) w0 = fma(v[i * vs], x[i * xs], w0);
+        const double w = (w0 + w1) * beta;
+        x[j * xs] -= w * v0;
+        for (i = j + 1; i < p; ++i) x[i * xs] = fma(-w, v[i * vs], x[i * xs]);
       }
     }
     tm.sync();  // column j is still intact up to here: everybody has read it
@@ -140,23 +163,39 @@ HSSB_HD void tm_qr(const Team& tm, Mat A, int p, int q, Mat Qt, int nq) {
 
 // X (n x ncols) <- L^-1 X, L lower triangular n x n (forward substitution, one thread per column)
 HSSB_HD void tm_trsm_lower(const Team& tm, Mat L, int n, Mat X, int ncols) {
-  for (int c = tm.tid; c < ncols; c += tm.nt)
+  for (int c = tm.tid; c < ncols; c += tm.nt) {
+    double* __restrict__ x = X.p + c * X.cs;  // L and X never overlap
+    const double* __restrict__ l = L.p;
     for (int i = 0; i < n; ++i) {
-      double s = X(i, c);
-      for (int j = 0; j < i; ++j) s = fma(-L(i, j), X(j, c), s);
-      X(i, c) = s / L(i, i);
+      double s0 = x[i * X.rs], s1 = 0.0;
+      int j = 0;
+      for (; j + 1 < i; j += 2) {
+        s0 = fma(-l[i * L.rs + j * L.cs], x[j * X.rs], s0);
+        s1 = fma(-l[i * L.rs + (j + 1) * L.cs], x[(j + 1) * X.rs], s1);
+      }
+      if (j < i) s0 = fma(-l[i * L.rs + j * L.cs], x[j * X.rs], s0);
+      x[i * X.rs] = (s0 + s1) / l[i * L.rs + i * L.cs];
     }
+  }
   tm.sync();
 }
 
 // X (n x ncols) <- R^-1 X, R upper triangular n x n (back substitution)
 HSSB_HD void tm_trsm_upper(const Team& tm, Mat R, int n, Mat X, int ncols) {
-  for (int c = tm.tid; c < ncols; c += tm.nt)
+  for (int c = tm.tid; c < ncols; c += tm.nt) {
+    double* __restrict__ x = X.p + c * X.cs;  // R and X never overlap
+    const double* __restrict__ r = R.p;
     for (int i = n - 1; i >= 0; --i) {
-      double s = X(i, c);
-      for (int j = i + 1; j < n; ++j) s = fma(-R(i, j), X(j, c), s);
-      X(i, c) = s / R(i, i);
+      double s0 = x[i * X.rs], s1 = 0.0;
+      int j = i + 1;
+      for (; j + 1 < n; j += 2) {
+        s0 = fma(-r[i * R.rs + j * R.cs], x[j * X.rs], s0);
+        s1 = fma(-r[i * R.rs + (j + 1) * R.cs], x[(j + 1) * X.rs], s1);
+      }
+      if (j < n) s0 = fma(-r[i * R.rs + j * R.cs], x[j * X.rs], s0);
+      x[i * X.rs] = (s0 + s1) / r[i * R.rs + i * R.cs];
     }
+  }
   tm.sync();
 }
 

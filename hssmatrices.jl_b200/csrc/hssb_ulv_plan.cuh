@@ -243,8 +243,8 @@ static int ulv_factor_device(hssb_matrix* H) {
   size_t widest = 1;
   for (auto& l : levels) widest = std::max(widest, l.size());
   const int64_t stride = round_up(ulv_scratch_len(H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW), 16);
-  // CTAs in flight: two per SM, fewer when the scratch of large nodes would not fit in 8 GiB
-  int ctas = (int)std::min<size_t>(widest, 148 * 2);
+  // CTAs in flight: three per SM (80 registers x 256 threads), fewer when the scratch of large nodes would not fit in 8 GiB
+  int ctas = (int)std::min<size_t>(widest, 148 * 3);
   while (ctas > 1 && (size_t)ctas * (size_t)stride * 8 > ((size_t)8 << 30)) ctas /= 2;
   UlvNode* d_nodes = nullptr;
   int32_t* d_list = nullptr;
