@@ -102,3 +102,73 @@ def test_solver_not_applicable(hb, oracle):
     S = hb.synthetic(256, 64, 4, 1, plan_only=True)                                             # no CPU fallback
     with pytest.raises(hb.HssbError):
         S.solve(np.zeros((256, 1)))
+
+
+def random_square_tree(oracle, rng, depth, root=True):
+    """Random HSS tree with square leaves of 1..9 rows at random depths, ranks 0..4 (so that some nodes
+    have rank >= size and are handed up whole, ulvfactor.jl:31-37), diagonally shifted."""
+    def rk():
+        return int(rng.integers(0, 5))
+
+    if depth == 0 or (not root and rng.random() < 0.3):
+        m = int(rng.integers(1, 10))
+        D = rng.standard_normal((m, m)) + 6.0 * np.eye(m)
+        if root:
+            return oracle.hss_leaf(D, rootnode=True)
+        return oracle.hss_leaf(D, rng.standard_normal((m, rk())) / 3, rng.standard_normal((m, rk())) / 3)
+    A11 = random_square_tree(oracle, rng, depth - 1, False)
+    A22 = random_square_tree(oracle, rng, depth - 1, False)
+    (kr1, kw1), (kr2, kw2) = oracle.gensize(A11), oracle.gensize(A22)
+    B12, B21 = rng.standard_normal((kr1, kw2)), rng.standard_normal((kr2, kw1))
+    if root:
+        return oracle.hss_branch(A11, A22, B12, B21, rootnode=True)
+    kr, kw = rk(), rk()
+    return oracle.hss_branch(A11, A22, B12, B21, rng.standard_normal((kr1, kr)) / 2, rng.standard_normal((kw1, kw)) / 2,
+                             rng.standard_normal((kr2, kr)) / 2, rng.standard_normal((kw2, kw)) / 2)
+
+
+def test_solve_plan_property(hb, oracle, ulv_oracle):
+    """Arbitrary (unbalanced, variable / zero / full rank) square trees: host-team factorisation + interpreted
+    solve plan against the dense solve and the oracle restatement."""
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+
+    @settings(max_examples=40, deadline=None, suppress_health_check=[HealthCheck.function_scoped_fixture])
+    @given(seed=st.integers(0, 2 ** 31 - 1), depth=st.integers(0, 4), k=st.integers(1, 4))
+    def run(seed, depth, k):
+        rng = np.random.default_rng(seed)
+        h = random_square_tree(oracle, rng, depth)
+        A = oracle.full(h)
+        n = A.shape[0]
+        B = rng.standard_normal((n, k))
+        cond = np.linalg.cond(A)
+        if cond > 1e8:
+            return
+        P = hb.pack(to_product_tree(hb, h), plan_only=True)
+        if P.ulv_info.supported == 0:      # a node would eliminate more rows than it has columns
+            P.close()
+            return
+        Z = solve_by_plan(P, B)
+        P.close()
+        ref = ulv_oracle.ulvfactsolve(h, B)
+        assert np.linalg.norm(A @ Z - B) <= 1e-13 * np.linalg.norm(A, 2) * np.linalg.norm(Z) * max(1.0, np.sqrt(n))
+        assert np.linalg.norm(Z - ref) <= 1e-13 * cond * np.linalg.norm(ref)
+
+    run()
+
+
+def test_options_and_info_on_plan_only_handles(hb, oracle):
+    P = hb.synthetic(1024, 128, 16, 2, plan_only=True)
+    ui = P.ulv_info
+    assert ui.supported == 1 and ui.factored == 0 and ui.pool_bytes > 0 and ui.flops_per_rhs > P.info.flops_per_rhs
+    assert P.get_option(hb.OPT_ADJOINT_TWIN) == 1
+    P.set_option(hb.OPT_ADJOINT_TWIN, 0)
+    assert P.get_option(hb.OPT_ADJOINT_TWIN) == 0
+    P.set_option(hb.OPT_PIPELINE_COLS, 12)
+    assert P.get_option(hb.OPT_PIPELINE_COLS) == 12
+    with pytest.raises(hb.HssbError):
+        P.ulv_factor()                      # no CPU fallback for the product path
+    with pytest.raises(hb.HssbError):
+        P.debug_ulv_pool()                  # not factorised yet
+    assert P.debug_ulv_pool(factor_on_host=True).size == ui.pool_bytes // 8
+    assert P.ulv_info.factored == 1
