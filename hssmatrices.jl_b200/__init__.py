@@ -23,7 +23,7 @@ LIB_PATH = os.path.join(_HERE, "lib", "libhssb200.so")
 
 __all__ = [
     "HssMatrix", "PackedHss", "DimensionMismatch", "HssbError", "bisection_cluster", "ClusterTree",
-    "isleaf", "isbranch", "size", "gensize", "rooted", "checkdims", "pack", "mul_", "synthetic",
+    "isleaf", "isbranch", "size", "gensize", "rooted", "checkdims", "pack", "mul_", "ulvfactsolve", "synthetic",
     "lib", "device_count", "measure_peak", "load",
 ]
 
@@ -299,6 +299,10 @@ class HssMatrix:
             return (self @ B.reshape(-1, 1)).reshape(-1)
         Cm = np.empty((size(self)[0], B.shape[1]), order="F")  # similar(): uninitialised
         return mul_(Cm, self, B, 1.0, 0.0)
+
+    def solve(self, B):
+        """`hssA \\ B` (src/hssmatrix.jl:234): ULV factorisation once per packed copy, then solves."""
+        return ulvfactsolve(self, B)
 
 
 def isleaf(h):  # src/hssmatrix.jl:88
@@ -670,6 +674,18 @@ class PackedHss:
         pool = np.zeros(pl.value)
         _check(lib().hssb_debug_pool(self._h, _ptr(pool), pool.size))
         return tasks, phases, pool
+
+
+def ulvfactsolve(hssA, B):
+    """`ulvfactsolve(hssA, b)` (src/ulvfactor.jl:10-19), i.e. `hssA \\ b`, for an HssMatrix or a PackedHss."""
+    if isinstance(hssA, PackedHss):
+        return hssA.solve(B)
+    B = np.asarray(B, dtype=np.float64)
+    if size(hssA, 0) != B.shape[0]:
+        raise DimensionMismatch(f"First dimension of B ({B.shape[0]}) does not match first dimension of A ({size(hssA, 0)})")
+    if hssA._packed is None:
+        hssA.repack()
+    return hssA._packed.solve(B)
 
 
 def mul_(Cm, hssA, B, alpha=1.0, beta=0.0):

@@ -41,6 +41,9 @@ def test_solve_matches_oracle(gpu, oracle, ulv_oracle, n, leafsize, nrhs, rmin, 
         assert np.linalg.norm(P @ X - A @ X) <= 1e-12 * np.linalg.norm(A @ X)
         # the device factor pool equals the host instantiation of the same node routine (up to fma contraction)
         dev = P.debug_ulv_pool()
+    Zt = gpu.ulvfactsolve(tree, B)           # the reference-named entry on the tree (packs on first use)
+    assert np.linalg.norm(Zt - Z) <= 1e-13 * np.linalg.norm(Z) + 1e-300
+    tree._packed.close()
     with gpu.pack(tree, plan_only=True) as Q:
         host = Q.debug_ulv_pool(factor_on_host=True)
     assert np.linalg.norm(dev - host) <= 1e-11 * np.linalg.norm(host)
