@@ -397,6 +397,24 @@ def main():
             "ulv_solve": solve,
         }
     # ---------------- CPU baseline (rank 0, N = 1 only) -------------------------
+    if rank == 0 and N == 1 and not args.no_cpu and isinstance(solve, dict) and "ms_per_solve" in solve:
+        # the CPU restatement of ulvfactsolve (factorises + solves per call, like ulvfactor.jl) on a 2^15-row subtree
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "oracle"))
+            import numpy as np
+            import hss_oracle as o
+            import hss_ulv_oracle as uo
+            nc = min(cfg["n"], 2 ** 15)
+            hc = o.synthetic_hss(nc, ls, r, SEED)
+            Bc = o.synth_x(SEED, nc, k)
+            tc0 = time.perf_counter()
+            uo.ulvfactsolve(hc, Bc)
+            tc = time.perf_counter() - tc0
+            solve["cpu_restatement"] = {"seconds_per_call_sample": tc, "sample_rows": nc,
+                                        "seconds_per_call_scaled": tc * cfg["n"] / nc, "kind": "port",
+                                        "note": "numpy restatement of ulvfactor.jl:10-107, scaled by the number of leaves"}
+        except Exception as e:   # the extra must never take the bench line down
+            solve["cpu_restatement"] = {"error": repr(e)}
     if rank == 0 and N == 1 and not args.no_cpu:
         s = cpu_sample(cfg, 3, 1, min(cfg["n"], 2 ** 17))
         out["cpu_baseline"] = {"value": s["gflops"], "unit": "GFLOP/s", "cores": s["cores"], "kind": "port",
