@@ -49,6 +49,22 @@ def test_solve_matches_oracle(gpu, oracle, ulv_oracle, n, leafsize, nrhs, rmin, 
     assert np.linalg.norm(dev - host) <= 1e-11 * np.linalg.norm(host)
 
 
+def test_reference_solver_assertion_restated(gpu, oracle, ulv_oracle):
+    """test/runtests.jl:66-67 through the C ABI: x = hssA \\ rhs against x0 = A \\ rhs on the reference's test
+    matrix (compress at tol 1e-6, leafsize 50): ||x0 - x|| / ||x0|| <= 50 * tol, and parity with the oracle."""
+    from test_ulv_cpu import reference_test_matrix
+    A = reference_test_matrix()
+    tol, c = 1e-6, 50.0
+    h = oracle.hss(A, leafsize=50, atol=tol, rtol=tol)
+    rhs = np.random.default_rng(1).standard_normal((2001, 5))
+    x0 = np.linalg.solve(A, rhs)
+    xr = ulv_oracle.ulvfactsolve(h, rhs)
+    with gpu.pack(to_product_tree(gpu, h)) as P:
+        x = P.solve(rhs)
+    assert np.linalg.norm(x0 - x) / np.linalg.norm(x0) <= c * tol
+    assert np.linalg.norm(xr - x) / np.linalg.norm(xr) <= 1e-12
+
+
 def test_solve_then_multiply_uniform(gpu, oracle, ulv_oracle):
     """Uniform synthetic trees (padded pool): A (A \\ B) == B with the product path, factor ahead of time."""
     import torch

@@ -172,3 +172,27 @@ def test_options_and_info_on_plan_only_handles(hb, oracle):
         P.debug_ulv_pool()                  # not factorised yet
     assert P.debug_ulv_pool(factor_on_host=True).size == ui.pool_bytes // 8
     assert P.ulv_info.factored == 1
+
+
+def reference_test_matrix():
+    """test/runtests.jl:17-30: one-sided Cauchy-like kernel on -1:0.001:1 (n = 2001)."""
+    x = np.linspace(-1, 1, 2001)
+    d = x[:, None] - x[None, :]
+    return np.where(d > 0, 0.001 / np.where(d > 0, d, 1.0), 2.0)
+
+
+def test_reference_solver_assertion_restated(hb, oracle, ulv_oracle):
+    """The reference's own check of `\\` (test/runtests.jl:66-67): hssA = compress(A) at tol 1e-6, leafsize 50,
+    rhs = randn(n, 5), x = hssA \\ rhs, x0 = A \\ rhs, ||x0 - x|| / ||x0|| <= 50 * tol — for the oracle
+    restatement and for the library's factorisation + solve plan."""
+    A = reference_test_matrix()
+    tol, c = 1e-6, 50.0
+    h = oracle.hss(A, leafsize=50, atol=tol, rtol=tol)
+    rhs = np.random.default_rng(1).standard_normal((2001, 5))
+    x0 = np.linalg.solve(A, rhs)
+    xr = ulv_oracle.ulvfactsolve(h, rhs)
+    assert np.linalg.norm(x0 - xr) / np.linalg.norm(x0) <= c * tol
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    Z = solve_by_plan(P, rhs)
+    assert np.linalg.norm(x0 - Z) / np.linalg.norm(x0) <= c * tol
+    assert np.linalg.norm(xr - Z) / np.linalg.norm(xr) <= 1e-12        # parity with the oracle on the same generators
