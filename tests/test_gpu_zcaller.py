@@ -1,0 +1,54 @@
+"""The reference's in-library caller of the hot path through the C ABI:
+randomized recompression of an operator that is itself an HSS matrix.  `randcompress_adaptive`
+(src/compression.jl:311-356) samples `Scol = A*Ω`, `Srow = A'*Ω` (:326-327) and, per iteration, checks
+`||Scol_test - hssA*Ω_test||` (:338-342) with nrhs = 20-30 — every one of those products runs on the GPU
+here (forward, transposed, and on a freshly re-packed result); the compression arithmetic itself is the
+oracle's restatement (CPU, not a GPU target)."""
+import numpy as np
+import pytest
+
+from test_plan_cpu import to_product_tree
+
+pytestmark = pytest.mark.gpu
+
+
+def test_randcompress_adaptive_caller(hb, oracle):
+    if hb.device_count() == 0:
+        pytest.skip("no B200 visible")
+    n, leafsize, kest, bs, tol = 2048, 64, 20, 20, 1e-6
+    A = oracle.cauchy_matrix(n)
+    cl = oracle.bisection_cluster(n, leafsize)
+    h0 = oracle.hss(A, leafsize, 1e-10, 1e-10)            # the operator: an accurate HSS form of A
+    with hb.pack(to_product_tree(hb, h0)) as P0:
+
+        class GpuOperator:                                  # LinearMap stand-in (src/linearmap.jl:31-32)
+            shape = (n, n)
+
+            def matmat(self, Om):                           # A*Ω   -> hssb_matmul
+                return P0 @ Om
+
+            def rmatmat(self, Om):                          # A'*Ω  -> hssb_matmul_t
+                return P0.tmatmul(Om)
+
+            def getindex(self, I, J):
+                return A[np.ix_(I, J)]
+
+        op = GpuOperator()
+        Om = np.random.default_rng(5).standard_normal((n, kest + 10))
+        assert np.linalg.norm(op.matmat(Om) - oracle.matmul(h0, Om)) <= 1e-12 * np.linalg.norm(oracle.matmul(h0, Om))
+        ref_t = oracle.matmul(oracle.adjoint(h0), Om)
+        assert np.linalg.norm(op.rmatmat(Om) - ref_t) <= 1e-12 * np.linalg.norm(ref_t)
+        h1 = oracle.randcompress(op, cl, cl, kest, atol=tol, rtol=tol, rng=np.random.default_rng(3))   # :278-294
+        # the error estimate of compression.jl:334-342, hssA*Ω_test on a freshly packed hssA
+        Om_test = np.random.default_rng(4).standard_normal((n, bs))
+        Scol_test = op.matmat(Om_test)
+        with hb.pack(to_product_tree(hb, h1)) as P1:
+            HOm = P1 @ Om_test
+        nrm = np.sqrt(1.0 / bs) * np.linalg.norm(Scol_test)
+        nrm_est = np.sqrt(1.0 / bs) * np.linalg.norm(Scol_test - HOm)
+        failed = nrm_est > tol and nrm_est > tol * nrm        # :342
+        assert not failed, (nrm_est, nrm)
+        # same estimate with the CPU restatement of the product
+        est_cpu = np.sqrt(1.0 / bs) * np.linalg.norm(oracle.matmul(h0, Om_test) - oracle.matmul(h1, Om_test))
+        assert abs(nrm_est - est_cpu) <= 1e-3 * est_cpu + 1e-12 * nrm   # a difference of nearly equal vectors: rounding of the products shows
+        assert np.linalg.norm(oracle.full(h1) - A) <= 50 * tol * np.linalg.norm(A)      # runtests.jl:39-40
