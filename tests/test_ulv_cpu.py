@@ -196,3 +196,26 @@ def test_reference_solver_assertion_restated(hb, oracle, ulv_oracle):
     Z = solve_by_plan(P, rhs)
     assert np.linalg.norm(x0 - Z) / np.linalg.norm(x0) <= c * tol
     assert np.linalg.norm(xr - Z) / np.linalg.norm(xr) <= 1e-12        # parity with the oracle on the same generators
+
+
+def test_solve_plan_rectangular_leaves(hb, oracle, ulv_oracle):
+    """Square matrix whose row and column cluster trees split differently (leaves with m != n, e.g. 251 x 250
+    next to 250 x 251): the reduced blocks stay rectangular up to the root."""
+    def cluster(lo, hi, leaf, bias):
+        n = hi - lo
+        if n <= leaf:
+            return oracle.ClusterTree((lo, hi))
+        mid = lo + (n + bias) // 2
+        return oracle.ClusterTree((lo, hi), cluster(lo, mid, leaf, 1 - bias), cluster(mid, hi, leaf, bias))
+
+    for n, leaf in ((501, 70), (333, 25)):
+        rng = np.random.default_rng(n)
+        h = oracle.random_hss(cluster(0, n, leaf, 1), cluster(0, n, leaf, 0), rng, 2, 6)
+        A = oracle.full(h)
+        B = rng.standard_normal((n, 3))
+        P = hb.pack(to_product_tree(hb, h), plan_only=True)
+        assert P.ulv_info.supported == 1
+        Z = solve_by_plan(P, B)
+        ref = ulv_oracle.ulvfactsolve(h, B)
+        assert np.linalg.norm(A @ Z - B) <= 1e-13 * np.linalg.norm(A, 2) * np.linalg.norm(Z)
+        assert np.linalg.norm(Z - ref) <= 1e-14 * np.linalg.cond(A) * np.linalg.norm(ref)
