@@ -16,14 +16,13 @@ import hss_oracle as o  # noqa: E402
 import plan_interp as pi  # noqa: E402
 
 
-def main():
-    dist.init_process_group("gloo")
-    rank, world = dist.get_rank(), dist.get_world_size()
-    n, ls, r, seed, k = 1024, 64, 6, 9, 5
+def sharded_product(rank, world, n, ls, r, seed, k, adjoint):
+    """One sharded product executed by the interpreter; adjoint=True runs the forward plan over the adjoint
+    twin pool (A' X on a sharded handle, hssb_matmul_t)."""
     P = hb.synthetic(n, ls, r, seed, shard_rank=rank, n_shards=world, plan_only=True)
     X = o.synth_x(seed, n, k, P.info.local_col0, P.info.local_n)
     Y = np.full((P.info.local_m, k), np.nan, order="F")
-    st = pi.ShardState(P, X, Y, k)
+    st = pi.ShardState(P, X, Y, k, P.debug_pool_t() if adjoint else None)
     for ph in [p for p in st.phases if not p.transposed]:
         if ph.kind == pi.PH_EXCHANGE:  # all-gather of the subtree-root Z blocks, in place in the Z workspace
             cnt, base = ph.xchg_slot_rows * k, ph.xchg_zoff * k
@@ -34,9 +33,19 @@ def main():
                 st.Z[base + g * cnt: base + (g + 1) * cnt] = sl.numpy()
         else:
             st.run_phase(ph, 1.0, 0.0)
-    ref = o.matmul(o.synthetic_hss(n, ls, r, seed), o.synth_x(seed, n, k))
+    h = o.synthetic_hss(n, ls, r, seed)
+    ref = o.matmul(o.adjoint(h) if adjoint else h, o.synth_x(seed, n, k))
     mine = ref[P.info.local_row0:P.info.local_row0 + P.info.local_m]
-    err = torch.tensor([np.linalg.norm(Y - mine) / np.linalg.norm(mine)])
+    return np.linalg.norm(Y - mine) / np.linalg.norm(mine)
+
+
+def main():
+    dist.init_process_group("gloo")
+    rank, world = dist.get_rank(), dist.get_world_size()
+    e = max(sharded_product(rank, world, 1024, 64, 6, 9, 5, False),      # any-shape layout
+            sharded_product(rank, world, 2048, 128, 16, 11, 3, False),   # padded (fixed-shape kernel) layout
+            sharded_product(rank, world, 2048, 128, 16, 11, 3, True))    # ... and its adjoint twin pool
+    err = torch.tensor([e])
     dist.all_reduce(err, op=dist.ReduceOp.MAX)
     dist.destroy_process_group()
     if rank == 0:
