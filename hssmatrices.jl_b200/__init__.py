@@ -19,7 +19,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libhssb200.so")
+LIB_PATH = os.environ.get("HSSB200_LIB") or os.path.join(_HERE, "lib", "libhssb200.so")  # same override as the Julia binding
 
 __all__ = [
     "HssMatrix", "PackedHss", "DimensionMismatch", "HssbError", "bisection_cluster", "ClusterTree",
