@@ -52,3 +52,17 @@ def test_randcompress_adaptive_caller(hb, oracle):
         est_cpu = np.sqrt(1.0 / bs) * np.linalg.norm(oracle.matmul(h0, Om_test) - oracle.matmul(h1, Om_test))
         assert abs(nrm_est - est_cpu) <= 1e-3 * est_cpu + 1e-12 * nrm   # a difference of nearly equal vectors: rounding of the products shows
         assert np.linalg.norm(oracle.full(h1) - A) <= 50 * tol * np.linalg.norm(A)      # runtests.jl:39-40
+
+
+def test_solve_golden_fixtures(hb, oracle):
+    """tests/golden/solve/*.npz (dense solves, make_golden_solve.py) through the C ABI: hssb_solve."""
+    if hb.device_count() == 0:
+        pytest.skip("no B200 visible")
+    import make_golden
+    from test_ulv_cpu import solve_golden_files
+    for f in solve_golden_files():
+        z = np.load(f)
+        h = make_golden.tree_from_npz(oracle, z)
+        with hb.pack(to_product_tree(hb, h)) as P:
+            got = P.solve(z["B"])
+        assert np.linalg.norm(got - z["Z"]) <= 1e-13 * float(z["cond"]) * np.linalg.norm(z["Z"]), f

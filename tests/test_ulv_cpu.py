@@ -219,3 +219,24 @@ def test_solve_plan_rectangular_leaves(hb, oracle, ulv_oracle):
         ref = ulv_oracle.ulvfactsolve(h, B)
         assert np.linalg.norm(A @ Z - B) <= 1e-13 * np.linalg.norm(A, 2) * np.linalg.norm(Z)
         assert np.linalg.norm(Z - ref) <= 1e-14 * np.linalg.cond(A) * np.linalg.norm(ref)
+
+
+def solve_golden_files():
+    import os
+    gdir = os.path.join(os.path.dirname(__file__), "golden", "solve")
+    return [os.path.join(gdir, f) for f in sorted(os.listdir(gdir)) if f.endswith(".npz")]
+
+
+def test_solve_golden_fixtures(hb, oracle, ulv_oracle):
+    """Committed vectors from DENSE solves (tests/golden/make_golden_solve.py): they guard the ULV oracle and the
+    library's factorisation + solve plan; tolerance = conditioning of the stored matrix."""
+    import make_golden
+    files = solve_golden_files()
+    assert len(files) >= 4
+    for f in files:
+        z = np.load(f)
+        h = make_golden.tree_from_npz(oracle, z)
+        tol = 1e-14 * float(z["cond"]) * np.linalg.norm(z["Z"])
+        assert np.linalg.norm(ulv_oracle.ulvfactsolve(h, z["B"]) - z["Z"]) <= tol, f
+        P = hb.pack(to_product_tree(hb, h), plan_only=True)
+        assert np.linalg.norm(solve_by_plan(P, z["B"]) - z["Z"]) <= tol, f
