@@ -501,6 +501,7 @@ static int plan_matrix(hssb_matrix* H) {
   build_plan(H);
   plan_fast_phases(H);
   build_plan_transposed(H);
+  H->ulv_task0 = (int64_t)H->tasks_host.size();
   build_plan_ulv(H);
   return HSSB_OK;
 }
@@ -1495,6 +1496,31 @@ int hssb_sync(hssb_matrix* h) {
   return HSSB_OK;
 }
 
+// HSSB_OPT_ULV_FAST: the ULV plan (tasks after ulv_task0, factor-pool layout, workspace rows) is rebuilt in
+// the other form; factors and graphs of the old form are dropped.
+static int rebuild_ulv_plan(hssb_matrix* h) {
+  if (h->ulv_task0 < 0) return HSSB_OK;
+  if (h->device >= 0) {
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    invalidate_graphs(h);
+    cudaFree(h->ulv_pool_dev);
+    h->ulv_pool_dev = nullptr;
+  }
+  h->ulv_pool_host.clear();
+  h->ulv_factored = false;
+  h->ws_ulv = false;  // the solve's workspace rows change with the form: re-sized by the next solve
+  h->tasks_host.resize((size_t)h->ulv_task0);
+  build_plan_ulv(h);
+  if (h->device >= 0 && !h->tasks_host.empty()) {
+    GTask* fresh = nullptr;
+    HSSB_CUDA(cudaMalloc(&fresh, h->tasks_host.size() * sizeof(GTask)));
+    HSSB_CUDA(cudaMemcpy(fresh, h->tasks_host.data(), h->tasks_host.size() * sizeof(GTask), cudaMemcpyHostToDevice));
+    cudaFree(h->tasks_dev);
+    h->tasks_dev = fresh;
+  }
+  return HSSB_OK;
+}
+
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_set_option: NULL handle");
   switch (opt) {
@@ -1504,6 +1530,13 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
     case HSSB_OPT_DEBUG: h->debug_mode = (int)value; break;
     case HSSB_OPT_PIPELINE_COLS: h->pipeline_cols = value; break;
     case HSSB_OPT_ADJOINT_TWIN: h->adjoint_twin = value != 0; break;
+    case HSSB_OPT_ULV_FAST: {
+      if (h->ulv_fast_form == (value != 0)) return HSSB_OK;
+      h->ulv_fast_form = value != 0;
+      if (h->device < 0) return rebuild_ulv_plan(h);
+      DeviceGuard dgu(h->device);
+      return rebuild_ulv_plan(h);
+    }
     default: HSSB_FAIL(HSSB_ERR_ARG, "hssb_set_option: unknown option %d", opt);
   }
   if (h->device < 0) return HSSB_OK;
@@ -1525,6 +1558,7 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
     case HSSB_OPT_DEBUG: return h->debug_mode;
     case HSSB_OPT_PIPELINE_COLS: return h->pipeline_cols;
     case HSSB_OPT_ADJOINT_TWIN: return !h->adjoint_twin ? 0 : (h->pool_t_dev ? 2 : 1);  // 2: built and in use
+    case HSSB_OPT_ULV_FAST: return !h->ulv_fast_form ? 0 : (h->ulv_ff ? 2 : 1);          // 2: the plan is in fast form
     default: return -1;
   }
 }

@@ -734,7 +734,8 @@ static int launch_fast(hssb_matrix* H, const Phase& ph, const CallParams& cp, cu
     cudaDeviceGetAttribute(&fs->num_sms, cudaDevAttrMultiProcessorCount, H->device);
     H->fast_state = fs;
   }
-  const int m = (int)H->uni_m, r = (int)H->uni_r;
+  // the product's phases run at the tree's (leaf size, rank); phases of the ULV solve carry their own shape
+  const int m = ph.fast_m ? ph.fast_m : (int)H->uni_m, r = ph.fast_r ? ph.fast_r : (int)H->uni_r;
   if (ph.fast == FAST_MERGE || ph.fast == FAST_TRANSLATE) {
     switch (r) {
       case 16: return launch_node<16>(H, ph, cp, st);

@@ -114,6 +114,12 @@ struct UlvNode {
   //   branch: one block per child s of k_s + kw_s columns.  pta: n_in x mk, ptb: n_in x n_out.
   int64_t az[2] = {-1, -1}, ac[2] = {-1, -1}, pta = -1, ptb = -1;
   int32_t ld_az = 2, ld_ac = 2, ld_pt = 2;
+  // "fast form" (uniform trees, HSSB_OPT_ULV_FAST): blocks shaped and padded (+4) for the fixed-shape
+  // kernels of the product.  Leaf: g = P'[:, :mk] T1 (n_in x m_in), so that the leaf output is
+  // Z[cols] = g b + ptb t, the shape of the product's leaf-down step, and zloc is never formed.
+  // Branch: P' split by rows into one pair of blocks per child (pta_c[s]: no_s x mk, ptb_c[s]: no_s x n_out).
+  int64_t g = -1, pta_c[2] = {-1, -1}, ptb_c[2] = {-1, -1};
+  int32_t ld_g = 2, ld_ptc[2] = {2, 2};
   // reduced generators handed to the parent (scratch that lives during the factorisation only)
   int64_t rD = -1, rU = -1, rV = -1;  // k x n_out, k x kr, n_out x kw (leading dimension = rows)
   // solve workspaces (row offsets): Z space holds zloc (mk rows) and c = [b; u] (k + kw rows),
@@ -131,6 +137,7 @@ struct Phase {
   int32_t level = 0;              // height (merge) or depth (translate)
   bool top = false;               // replicated top-tree phase
   int fast = 0;                   // fixed-shape kernel id (0 = generic)
+  int32_t fast_m = 0, fast_r = 0; // shape the fixed-shape kernel is instantiated for (0 = the tree's leaf size / rank)
 };
 
 }  // namespace hssb
@@ -153,6 +160,9 @@ struct hssb_matrix {
   double* ulv_pool_dev = nullptr;
   std::vector<double> ulv_pool_host;  // plan-only handles: factorised on the host by the test hook
   bool ulv_factored = false;
+  bool ulv_fast_form = false;         // HSSB_OPT_ULV_FAST requested
+  bool ulv_ff = false;                // ... and the tree qualifies: the ULV plan is in fast form
+  int64_t ulv_task0 = -1;             // first ULV task in tasks_host (the ULV plan can be rebuilt)
   std::vector<hssb::GTask> tasks_host;
   hssb::GTask* tasks_dev = nullptr;
   double* pool_dev = nullptr;

@@ -308,8 +308,15 @@ HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double*
     tm_gemm(tm, T23.sub(k, 0), Vq.t(), T1, kw, m, mk, 1.0, 0.0); // T3 = Vq_top' T1
     tm_copy(tm, colmajor(cx.red + u.rD, k > 0 ? k : 1), L2.sub(0, mk), k, no);
     tm_copy(tm, colmajor(cx.red + u.rV, no > 0 ? no : 1), Vq.sub(mk, 0), no, kw);
-    tm_copy(tm, colmajor(cx.fpool + u.pta, u.ld_pt), P.t(), n, mk);             // P'[:, :mk]
-    tm_copy(tm, colmajor(cx.fpool + u.ptb, u.ld_pt), P.t().sub(0, mk), n, no);  // P'[:, mk:]
+    if (u.pta >= 0) tm_copy(tm, colmajor(cx.fpool + u.pta, u.ld_pt), P.t(), n, mk);             // P'[:, :mk]
+    if (u.ptb >= 0) tm_copy(tm, colmajor(cx.fpool + u.ptb, u.ld_pt), P.t().sub(0, mk), n, no);  // P'[:, mk:]
+    // fast form (see UlvNode): the leaf output operator g = P'[:, :mk] T1, and P' split by child rows
+    if (u.g >= 0) tm_gemm(tm, colmajor(cx.fpool + u.g, u.ld_g), P.t(), T1, n, m, mk, 1.0, 0.0);
+    for (int c = 0; c < 2; ++c) {
+      const int r0 = c ? u.no1 : 0, rows = c ? u.no2 : u.no1;
+      if (u.pta_c[c] >= 0) tm_copy(tm, colmajor(cx.fpool + u.pta_c[c], u.ld_ptc[c]), P.t().sub(r0, 0), rows, mk);
+      if (u.ptb_c[c] >= 0) tm_copy(tm, colmajor(cx.fpool + u.ptb_c[c], u.ld_ptc[c]), P.t().sub(r0, mk), rows, no);
+    }
   } else {  // cannot be compressed (ulvfactor.jl:31-37): everything is handed to the parent
     tm_eye(tm, T23, k, m, 1.0);
     tm_eye(tm, T23.sub(k, 0), kw, m, 0.0);
@@ -321,7 +328,7 @@ HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double*
 
   // ---- the matrices of the solve's upsweep
   if (u.is_leaf) {
-    if (mk > 0) tm_copy(tm, colmajor(cx.fpool + u.az[0], u.ld_az), T1, mk, m);
+    if (mk > 0 && u.az[0] >= 0) tm_copy(tm, colmajor(cx.fpool + u.az[0], u.ld_az), T1, mk, m);
     tm_copy(tm, colmajor(cx.fpool + u.ac[0], u.ld_ac), T23, k + kw, m);
   } else {
     if (mk > 0)

@@ -56,10 +56,26 @@ static void build_plan_ulv(hssb_matrix* H) {
     }
   }
 
+  // ---- fast form (HSSB_OPT_ULV_FAST): on a uniform tree every block of the solve has the shape of a
+  // block of the product (leaf size m, rank r: [T2; T3] is 2r x m like V', g is m x m like D, ptb m x r
+  // like U, the c merges are 2r x 2r, the top-down blocks r x r), so with the padded (+4) layout the
+  // fixed-shape kernels of hssb_fast.cuh can run the solve's big phases.
+  bool ff = H->ulv_fast_form && H->padded && !uv[0].is_leaf;
+  if (ff) {
+    const int32_t m = (int32_t)H->uni_m, r = (int32_t)H->uni_r;
+    for (const UlvNode& u : uv) {
+      if (u.is_root) ff = ff && u.m_in == 2 * r && u.n_in == 2 * r;
+      else if (u.is_leaf) ff = ff && u.m_in == m && u.n_in == m && u.kr == r && u.kw == r && u.mk == m - r && u.n_out == r;
+      else ff = ff && u.m_in == 2 * r && u.n_in == 2 * r && u.kr == r && u.kw == r && u.mk == r && u.n_out == r;
+    }
+  }
+  H->ulv_ff = ff;
+  auto ld_of = [&](int64_t rows) { return (int32_t)std::max<int64_t>(ff ? rows + 4 : round_up(rows, 2), 2); };
+
   // ---- factor pool / reduced-generator scratch / workspaces
   int64_t off = 0, red = 0, zo = 0, fo = 0;
   auto place = [&](int64_t rows, int64_t cols, int32_t& ld) {
-    ld = (int32_t)std::max<int64_t>(round_up(rows, 2), 2);
+    ld = ld_of(rows);
     if (rows == 0 || cols == 0) return (int64_t)-1;
     const int64_t at = off;
     off += round_up((int64_t)ld * cols, 16);
@@ -73,8 +89,9 @@ static void build_plan_ulv(hssb_matrix* H) {
     const int64_t rows_c = u.is_root ? u.n_in : u.k + u.kw;
     int32_t ld_tmp;
     if (u.is_leaf) {
-      u.az[0] = place(u.mk, u.m_in, u.ld_az);
+      if (!ff) u.az[0] = place(u.mk, u.m_in, u.ld_az);
       u.ac[0] = place(rows_c, u.m_in, u.ld_ac);
+      if (ff) u.g = place(u.n_in, u.m_in, u.ld_g);
     } else {
       u.az[0] = place(u.mk, u.k1 + u.kw1, u.ld_az);
       u.az[1] = place(u.mk, u.k2 + u.kw2, ld_tmp);
@@ -82,15 +99,22 @@ static void build_plan_ulv(hssb_matrix* H) {
       u.ac[1] = place(rows_c, u.k2 + u.kw2, ld_tmp);
     }
     if (!u.is_root) {
-      u.pta = place(u.n_in, u.mk, u.ld_pt);
-      u.ptb = place(u.n_in, u.n_out, ld_tmp);
+      if (ff && !u.is_leaf) {  // P' split by rows: one pair of r x r blocks per child
+        u.pta_c[0] = place(u.no1, u.mk, u.ld_ptc[0]);
+        u.ptb_c[0] = place(u.no1, u.n_out, ld_tmp);
+        u.pta_c[1] = place(u.no2, u.mk, u.ld_ptc[1]);
+        u.ptb_c[1] = place(u.no2, u.n_out, ld_tmp);
+      } else {
+        if (!ff) u.pta = place(u.n_in, u.mk, u.ld_pt);
+        u.ptb = place(u.n_in, u.n_out, ff ? u.ld_pt : ld_tmp);
+      }
       u.rD = red; red += (int64_t)u.k * u.n_out;
       u.rU = red; red += (int64_t)u.k * u.kr;
       u.rV = red; red += (int64_t)u.n_out * u.kw;
-      u.ld_zloc = (int32_t)std::max<int64_t>(round_up(u.mk, 2), 2);
-      u.ld_c = (int32_t)std::max<int64_t>(round_up(u.k + u.kw, 2), 2);
-      u.ld_t = (int32_t)std::max<int64_t>(round_up(u.n_out, 2), 2);
-      u.zloc = zo; zo += u.ld_zloc;
+      u.ld_zloc = ld_of(u.mk);
+      u.ld_c = ld_of(u.k + u.kw);
+      u.ld_t = ld_of(u.n_out);
+      if (!(ff && u.is_leaf)) { u.zloc = zo; zo += u.ld_zloc; }  // fast-form leaves never form zloc
       u.c = zo; zo += u.ld_c;
       u.t = fo; fo += u.ld_t;
     }
@@ -135,7 +159,7 @@ static void build_plan_ulv(hssb_matrix* H) {
     for (int64_t li : H->leaves) {
       const UlvNode& u = uv[(size_t)li];
       const Node& t = nodes[(size_t)li];
-      for (int part = 0; part < 2; ++part) {
+      for (int part = ff ? 1 : 0; part < 2; ++part) {  // fast form: c only, zloc is folded into the leaf output
         GTask g = blank();
         g.a0 = part ? u.ac[0] : u.az[0]; g.lda0 = part ? u.ld_ac : u.ld_az;
         g.sb0 = SRC_X; g.b0 = t.row0; g.K0 = u.m_in;
@@ -153,12 +177,23 @@ static void build_plan_ulv(hssb_matrix* H) {
         const UlvNode& u = uv[i];
         GTask g = merge_rows(u, u.az, u.ld_az, 0, u.mk);
         g.sc = SRC_Z; g.c = u.zloc; g.ldc = u.ld_zloc;
-        push(g);
+        if (!ff) push(g);
         g = merge_rows(u, u.ac, u.ld_ac, 0, u.k + u.kw);
         g.sc = SRC_Z; g.c = u.c; g.ldc = u.ld_c;
         push(g);
       }
       add_phase(H, PH_MERGE, h, false, batch, &out);
+      if (ff) {  // the square 2r x 2r merges above form a fixed-shape phase of their own; zloc (r x 2r blocks) follows
+        for (size_t i = 0; i < nodes.size(); ++i) {
+          const Node& t = nodes[i];
+          if (t.leaf || t.height != h || t.parent < 0) continue;
+          const UlvNode& u = uv[i];
+          GTask g = merge_rows(u, u.az, u.ld_az, 0, u.mk);
+          g.sc = SRC_Z; g.c = u.zloc; g.ldc = u.ld_zloc;
+          push(g);
+        }
+        add_phase(H, PH_MERGE, h, false, batch, &out);
+      }
     }
     // root: [t1; t2] = D^-1 b (ulvfactor.jl:83), rows split between the children
     {
@@ -181,6 +216,13 @@ static void build_plan_ulv(hssb_matrix* H) {
       if (u.ptb >= 0) { g.a1 = u.ptb + r0; g.lda1 = u.ld_pt; g.sb1 = SRC_F; g.b1 = u.t; g.ldb1 = u.ld_t; g.K1 = u.n_out; }
       return g;
     };
+    auto down_child = [&](const UlvNode& u, int s) {  // fast form: child s's rows of P' are blocks of their own
+      GTask g = blank();
+      g.M = s ? u.no2 : u.no1;
+      if (u.pta_c[s] >= 0) { g.a0 = u.pta_c[s]; g.lda0 = u.ld_ptc[s]; g.sb0 = SRC_Z; g.b0 = u.zloc; g.ldb0 = u.ld_zloc; g.K0 = u.mk; }
+      if (u.ptb_c[s] >= 0) { g.a1 = u.ptb_c[s]; g.lda1 = u.ld_ptc[s]; g.sb1 = SRC_F; g.b1 = u.t; g.ldb1 = u.ld_t; g.K1 = u.n_out; }
+      return g;
+    };
     for (int d = 1; d <= (int)H->depth; ++d) {
       for (size_t i = 0; i < nodes.size(); ++i) {
         const Node& t = nodes[i];
@@ -188,10 +230,10 @@ static void build_plan_ulv(hssb_matrix* H) {
         const UlvNode& u = uv[i];
         const UlvNode& c1 = uv[(size_t)u.left];
         const UlvNode& c2 = uv[(size_t)u.right];
-        GTask g = down(u, 0, u.no1);
+        GTask g = ff ? down_child(u, 0) : down(u, 0, u.no1);
         g.sc = SRC_F; g.c = c1.t; g.ldc = c1.ld_t;
         push(g);
-        g = down(u, u.no1, u.no2);
+        g = ff ? down_child(u, 1) : down(u, u.no1, u.no2);
         g.sc = SRC_F; g.c = c2.t; g.ldc = c2.ld_t;
         push(g);
       }
@@ -200,10 +242,41 @@ static void build_plan_ulv(hssb_matrix* H) {
     for (int64_t li : H->leaves) {
       const UlvNode& u = uv[(size_t)li];
       GTask g = down(u, 0, u.n_in);
+      if (ff) {  // Z[cols] = g b + ptb t: the shape of the product's leaf-down step (Y = D X + U F)
+        g = blank();
+        g.M = u.n_in;
+        g.a0 = u.g; g.lda0 = u.ld_g; g.sb0 = SRC_X; g.b0 = nodes[(size_t)li].row0; g.K0 = u.m_in;
+        g.a1 = u.ptb; g.lda1 = u.ld_pt; g.sb1 = SRC_F; g.b1 = u.t; g.ldb1 = u.ld_t; g.K1 = u.n_out;
+        g.epilogue = 1;  // alpha = 1, beta = 0 in hssb_solve
+      }
       g.sc = SRC_Y; g.c = nodes[(size_t)li].col0;
       push(g);
     }
     add_phase(H, PH_LEAF_DOWN, 0, false, batch, &out);
+  }
+  if (ff) {  // tag the phases a fixed-shape kernel of the product can run (same checks as plan_fast_phases)
+    const int32_t m = (int32_t)H->uni_m, r = (int32_t)H->uni_r;
+    auto node_r = [](int32_t R) { return R == 16 || R == 32 || R == 64; };
+    for (Phase& ph : out) {
+      const GTask* tk = H->tasks_host.data() + ph.task0;
+      bool up = ph.kind == PH_LEAF_UP && fast_shape_supported(m, 2 * r), mc = ph.kind == PH_MERGE && node_r(2 * r);
+      bool tr = ph.kind == PH_TRANSLATE && node_r(r), dn = ph.kind == PH_LEAF_DOWN && fast_shape_supported(m, r);
+      for (int64_t i = 0; i < ph.ntasks; ++i) {
+        const GTask& g = tk[i];
+        const bool plain = !g.ta0 && !g.ta1 && g.a0 >= 0;
+        up = up && plain && g.M == 2 * r && g.K0 == m && g.K1 == 0 && g.lda0 == 2 * r + 4 && g.ldc == 2 * r + 4 && g.sb0 == SRC_X && g.sc == SRC_Z;
+        mc = mc && plain && g.a1 >= 0 && g.M == 2 * r && g.K0 == 2 * r && g.K1 == 2 * r && g.lda0 == 2 * r + 4 && g.lda1 == 2 * r + 4 &&
+             g.ldb0 == 2 * r + 4 && g.ldb1 == 2 * r + 4 && g.ldc == 2 * r + 4 && g.sb0 == SRC_Z && g.sb1 == SRC_Z && g.sc == SRC_Z;
+        tr = tr && plain && g.a1 >= 0 && g.M == r && g.K0 == r && g.K1 == r && g.lda0 == r + 4 && g.lda1 == r + 4 && g.ldb0 == r + 4 &&
+             g.ldb1 == r + 4 && g.ldc == r + 4 && g.sb0 == SRC_Z && g.sb1 == SRC_F && g.sc == SRC_F;
+        dn = dn && plain && g.a1 >= 0 && g.M == m && g.K0 == m && g.K1 == r && g.lda0 == m + 4 && g.lda1 == m + 4 && g.ldb1 == r + 4 &&
+             g.sb0 == SRC_X && g.sb1 == SRC_F && g.sc == SRC_Y;
+      }
+      if (up) { ph.fast = FAST_LEAF_UP; ph.fast_m = m; ph.fast_r = 2 * r; }
+      else if (mc) { ph.fast = FAST_MERGE; ph.fast_r = 2 * r; }
+      else if (tr) { ph.fast = FAST_TRANSLATE; ph.fast_r = r; }
+      else if (dn) { ph.fast = FAST_LEAF_DOWN; ph.fast_m = m; ph.fast_r = r; }
+    }
   }
   H->ulv_flops_per_rhs = flops;
   H->ulv = std::move(uv);

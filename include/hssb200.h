@@ -201,6 +201,12 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
 #define HSSB_OPT_PIPELINE_COLS 6 /* host entry: right-hand sides per pipelined block (0 = automatic)  */
 #define HSSB_OPT_ADJOINT_TWIN 7  /* 1 (default): hssb_matmul_t of a uniform tree keeps a transposed twin of the pool on the device;
                                     0: release it / never build it.  hssb_get_option returns 2 once the twin exists. */
+#define HSSB_OPT_ULV_FAST 8      /* EXPERIMENTAL, default 0.  1: on uniform trees lay the ULV factors out in the shapes and padding of
+                                    the product's blocks ("fast form": the leaf output becomes g b + ptb t like Y = D X + U F, zloc is
+                                    not formed at the leaves, P' is split per child) so that the fixed-shape DMMA kernels run the solve's
+                                    leaf phases, square merges and top-down steps.  Rebuilds the solve plan and drops existing factors.
+                                    hssb_get_option returns 2 when the plan is in fast form.  Plan and factorisation are covered by the
+                                    CPU tests; the kernels' use on this plan has not been run on a GPU yet.                            */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */

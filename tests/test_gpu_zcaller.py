@@ -4,6 +4,8 @@ randomized recompression of an operator that is itself an HSS matrix.  `randcomp
 `||Scol_test - hssA*Ω_test||` (:338-342) with nrhs = 20-30 — every one of those products runs on the GPU
 here (forward, transposed, and on a freshly re-packed result); the compression arithmetic itself is the
 oracle's restatement (CPU, not a GPU target)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -66,3 +68,22 @@ def test_solve_golden_fixtures(hb, oracle):
         with hb.pack(to_product_tree(hb, h)) as P:
             got = P.solve(z["B"])
         assert np.linalg.norm(got - z["Z"]) <= 1e-13 * float(z["cond"]) * np.linalg.norm(z["Z"]), f
+
+
+@pytest.mark.skipif(os.environ.get("HSSB_TEST_ULV_FAST") != "1",
+                    reason="experimental HSSB_OPT_ULV_FAST: fixed-shape kernels on the solve plan, not yet run on a GPU "
+                           "(set HSSB_TEST_ULV_FAST=1)")
+def test_ulv_fast_form_on_device(hb, oracle):
+    if hb.device_count() == 0:
+        pytest.skip("no B200 visible")
+    for n, ls, r, k in ((4096, 128, 32, 64), (4096, 128, 16, 20), (4096, 256, 32, 32)):
+        with hb.synthetic(n, ls, r, 5) as P:
+            B = oracle.synth_x(5, n, k)
+            Z0 = P.solve(B)
+            P.set_option(hb.OPT_ULV_FAST, 1)
+            assert P.get_option(hb.OPT_ULV_FAST) == 2
+            Z1 = P.solve(B)
+            assert np.linalg.norm(Z1 - Z0) <= 1e-9 * np.linalg.norm(Z0)
+            R = P @ Z1 - B
+            A = oracle.full(oracle.synthetic_hss(n, ls, r, 5))
+            assert np.linalg.norm(R) <= 1e-12 * np.linalg.norm(A, 2) * np.linalg.norm(Z1)

@@ -240,3 +240,43 @@ def test_solve_golden_fixtures(hb, oracle, ulv_oracle):
         assert np.linalg.norm(ulv_oracle.ulvfactsolve(h, z["B"]) - z["Z"]) <= tol, f
         P = hb.pack(to_product_tree(hb, h), plan_only=True)
         assert np.linalg.norm(solve_by_plan(P, z["B"]) - z["Z"]) <= tol, f
+
+
+@pytest.mark.parametrize("n,ls,r", [(2048, 128, 16), (2048, 128, 32), (4096, 256, 32), (1024, 128, 64)])
+def test_ulv_fast_form_plan(hb, oracle, ulv_oracle, n, ls, r):
+    """HSSB_OPT_ULV_FAST (experimental): the solve plan of a uniform tree rebuilt in the shapes / padding of the
+    product's blocks.  Same solution as the default form; the phases a fixed-shape kernel can take are tagged
+    (leaf-up as V'-like 2r x m, square 2r x 2r merges, r x r top-down steps, leaf-down as D/U-like); fewer
+    flops (zloc is folded into the leaf output operator); switching back restores the default plan bit for bit."""
+    seed = 4
+    h = oracle.synthetic_hss(n, ls, r, seed)
+    B = oracle.synth_x(seed, n, 3)
+    ref = ulv_oracle.ulvfactsolve(h, B)
+    P = hb.synthetic(n, ls, r, seed, plan_only=True)
+    Z0 = solve_by_plan(P, B)
+    info0 = (P.ulv_info.flops_per_rhs, P.ulv_info.pool_bytes)
+    P.set_option(hb.OPT_ULV_FAST, 1)
+    assert P.get_option(hb.OPT_ULV_FAST) == 2 and P.ulv_info.factored == 0
+    Z1 = solve_by_plan(P, B)
+    tol = 1e-10 * np.linalg.norm(ref)   # these seeded matrices have cond ~ 1e5..1e6; measured 3e-13..5e-13
+    assert np.linalg.norm(Z0 - ref) <= tol and np.linalg.norm(Z1 - ref) <= tol
+    assert P.ulv_info.flops_per_rhs <= info0[0]
+    _, phases, _ = P.debug_plan()
+    fast = {(ph.kind, ph.fast) for ph in phases if ph.transposed == 2}
+    assert (4, 4) in fast and (3, 3) in fast                      # leaf-down and the r x r top-down steps
+    assert ((0, 1) in fast) == (2 * r <= 64) and ((1, 2) in fast) == (2 * r <= 64)   # V'-like leaf-up / square merges need 2r <= 64
+    assert (3, 0) in fast                                          # the root stays on the any-shape kernel
+    P.set_option(hb.OPT_ULV_FAST, 0)
+    assert P.get_option(hb.OPT_ULV_FAST) == 0
+    assert np.array_equal(solve_by_plan(P, B), Z0)
+
+
+def test_ulv_fast_form_needs_uniform_tree(hb, oracle):
+    rng = np.random.default_rng(8)
+    cl = oracle.bisection_cluster(300, 40)
+    P = hb.pack(to_product_tree(hb, oracle.random_hss(cl, cl, rng, 1, 5)), plan_only=True)
+    P.set_option(hb.OPT_ULV_FAST, 1)
+    assert P.get_option(hb.OPT_ULV_FAST) == 1        # requested, but the plan stays in the default form
+    B = rng.standard_normal((300, 2))
+    Z = solve_by_plan(P, B)
+    assert np.isfinite(Z).all()

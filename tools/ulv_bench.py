@@ -7,11 +7,16 @@ sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle")]
 import numpy as np
 import torch
 import hssb200 as hb
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 2 ** 20
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+n = int(args[0]) if args else 2 ** 20
+FAST = "--fast" in sys.argv   # experimental HSSB_OPT_ULV_FAST: fixed-shape kernels on the solve plan
 ls, r, k, seed = 128, 32, 64, 3
 P = hb.synthetic(n, ls, r, seed)
 s = torch.cuda.Stream(); torch.cuda.set_stream(s)
 P.set_option(hb.OPT_USE_GRAPH, 1)
+if FAST:
+    P.set_option(hb.OPT_ULV_FAST, 1)
+    print("fast form:", P.get_option(hb.OPT_ULV_FAST) == 2)
 ui = P.ulv_info
 print(f"n {n}: factor pool {ui.pool_bytes * 1e-9:.2f} GB (generators {P.info.pool_bytes * 1e-9:.2f} GB), solve flops/rhs {ui.flops_per_rhs:.3e} (product {P.info.flops_per_rhs:.3e})")
 torch.cuda.synchronize(); t0 = time.perf_counter()
