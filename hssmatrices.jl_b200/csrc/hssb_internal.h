@@ -114,18 +114,18 @@ struct UlvNode {
   //   branch: one block per child s of k_s + kw_s columns.  pta: n_in x mk, ptb: n_in x n_out.
   int64_t az[2] = {-1, -1}, ac[2] = {-1, -1}, pta = -1, ptb = -1;
   int32_t ld_az = 2, ld_ac = 2, ld_pt = 2;
-  // "fast form" (uniform trees, HSSB_OPT_ULV_FAST): blocks shaped and padded (+4) for the fixed-shape
-  // kernels of the product.  Leaf: g = P'[:, :mk] T1 (n_in x m_in), so that the leaf output is
-  // Z[cols] = g b + ptb t, the shape of the product's leaf-down step, and zloc is never formed.
-  // Branch: P' split by rows into one pair of blocks per child (pta_c[s]: no_s x mk, ptb_c[s]: no_s x n_out).
-  int64_t g = -1, pta_c[2] = {-1, -1}, ptb_c[2] = {-1, -1};
-  int32_t ld_g = 2, ld_ptc[2] = {2, 2};
   // reduced generators handed to the parent (scratch that lives during the factorisation only)
   int64_t rD = -1, rU = -1, rV = -1;  // k x n_out, k x kr, n_out x kw (leading dimension = rows)
   // solve workspaces (row offsets): Z space holds zloc (mk rows) and c = [b; u] (k + kw rows),
   // F space holds t (the n_out trailing unknowns, written by the parent)
   int64_t zloc = -1, c = -1, t = -1;
   int32_t ld_zloc = 2, ld_c = 2, ld_t = 2;
+  // "fast form" (uniform trees, HSSB_OPT_ULV_FAST): blocks shaped and padded (+4) for the fixed-shape
+  // kernels of the product.  Leaf: g = P'[:, :mk] T1 (n_in x m_in), so that the leaf output is
+  // Z[cols] = g b + ptb t, the shape of the product's leaf-down step, and zloc is never formed.
+  // Branch: P' split by rows into one pair of blocks per child (pta_c[s]: no_s x mk, ptb_c[s]: no_s x n_out).
+  int64_t g = -1, pta_c[2] = {-1, -1}, ptb_c[2] = {-1, -1};
+  int32_t ld_g = 2, ld_ptc[2] = {2, 2};
 };
 
 enum PhaseKind : int { PH_LEAF_UP = 0, PH_MERGE, PH_EXCHANGE, PH_TRANSLATE, PH_LEAF_DOWN, PH_XCHG_ACK };

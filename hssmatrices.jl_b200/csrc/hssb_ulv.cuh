@@ -231,7 +231,10 @@ HSSB_HD void ulv_fold(const Team& tm, const UlvNode& u, Mat T, int rows, Mat G12
   tm_gemm(tm, A2.sub(0, u.k2), T, G12, rows, u.kw2, u.k1, -1.0, 0.0);
 }
 
-// Factorises one node.  `s` is the team's scratch (ulv_scratch_len doubles).
+// Factorises one node.  `s` is the team's scratch (ulv_scratch_len doubles).  FF: the plan is in fast
+// form (UlvNode::g, pta_c, ptb_c); the default form is a separate instantiation so that its code does not
+// change with the experimental one.
+template <bool FF>
 HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double* s) {
   const UlvNode& u = cx.nodes[node];
   const int m = u.m_in, n = u.n_in, kr = u.kr, kw = u.kw, k = u.k, mk = u.mk, no = u.n_out;
@@ -308,14 +311,17 @@ HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double*
     tm_gemm(tm, T23.sub(k, 0), Vq.t(), T1, kw, m, mk, 1.0, 0.0); // T3 = Vq_top' T1
     tm_copy(tm, colmajor(cx.red + u.rD, k > 0 ? k : 1), L2.sub(0, mk), k, no);
     tm_copy(tm, colmajor(cx.red + u.rV, no > 0 ? no : 1), Vq.sub(mk, 0), no, kw);
-    if (u.pta >= 0) tm_copy(tm, colmajor(cx.fpool + u.pta, u.ld_pt), P.t(), n, mk);             // P'[:, :mk]
-    if (u.ptb >= 0) tm_copy(tm, colmajor(cx.fpool + u.ptb, u.ld_pt), P.t().sub(0, mk), n, no);  // P'[:, mk:]
-    // fast form (see UlvNode): the leaf output operator g = P'[:, :mk] T1, and P' split by child rows
-    if (u.g >= 0) tm_gemm(tm, colmajor(cx.fpool + u.g, u.ld_g), P.t(), T1, n, m, mk, 1.0, 0.0);
-    for (int c = 0; c < 2; ++c) {
-      const int r0 = c ? u.no1 : 0, rows = c ? u.no2 : u.no1;
-      if (u.pta_c[c] >= 0) tm_copy(tm, colmajor(cx.fpool + u.pta_c[c], u.ld_ptc[c]), P.t().sub(r0, 0), rows, mk);
-      if (u.ptb_c[c] >= 0) tm_copy(tm, colmajor(cx.fpool + u.ptb_c[c], u.ld_ptc[c]), P.t().sub(r0, mk), rows, no);
+    if constexpr (!FF) {
+      tm_copy(tm, colmajor(cx.fpool + u.pta, u.ld_pt), P.t(), n, mk);             // P'[:, :mk]
+      tm_copy(tm, colmajor(cx.fpool + u.ptb, u.ld_pt), P.t().sub(0, mk), n, no);  // P'[:, mk:]
+    } else {  // fast form (see UlvNode): the leaf output operator g = P'[:, :mk] T1, and P' split by child rows
+      if (u.ptb >= 0) tm_copy(tm, colmajor(cx.fpool + u.ptb, u.ld_pt), P.t().sub(0, mk), n, no);
+      if (u.g >= 0) tm_gemm(tm, colmajor(cx.fpool + u.g, u.ld_g), P.t(), T1, n, m, mk, 1.0, 0.0);
+      for (int c = 0; c < 2; ++c) {
+        const int r0 = c ? u.no1 : 0, rows = c ? u.no2 : u.no1;
+        if (u.pta_c[c] >= 0) tm_copy(tm, colmajor(cx.fpool + u.pta_c[c], u.ld_ptc[c]), P.t().sub(r0, 0), rows, mk);
+        if (u.ptb_c[c] >= 0) tm_copy(tm, colmajor(cx.fpool + u.ptb_c[c], u.ld_ptc[c]), P.t().sub(r0, mk), rows, no);
+      }
     }
   } else {  // cannot be compressed (ulvfactor.jl:31-37): everything is handed to the parent
     tm_eye(tm, T23, k, m, 1.0);
@@ -328,7 +334,7 @@ HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double*
 
   // ---- the matrices of the solve's upsweep
   if (u.is_leaf) {
-    if (mk > 0 && u.az[0] >= 0) tm_copy(tm, colmajor(cx.fpool + u.az[0], u.ld_az), T1, mk, m);
+    if (mk > 0 && (!FF || u.az[0] >= 0)) tm_copy(tm, colmajor(cx.fpool + u.az[0], u.ld_az), T1, mk, m);
     tm_copy(tm, colmajor(cx.fpool + u.ac[0], u.ld_ac), T23, k + kw, m);
   } else {
     if (mk > 0)
@@ -347,7 +353,18 @@ ulv_factor_kernel(UlvCtx cx, const int32_t* __restrict__ level_nodes, int count,
   const Team tm{(int)threadIdx.x, (int)blockDim.x};
   double* s = scratch + (int64_t)blockIdx.x * scratch_stride;
   for (int i = blockIdx.x; i < count; i += gridDim.x) {
-    ulv_factor_node(tm, cx, level_nodes[i], s);
+    ulv_factor_node<false>(tm, cx, level_nodes[i], s);
+    __syncthreads();
+  }
+}
+
+// the same for a plan in fast form (HSSB_OPT_ULV_FAST)
+__global__ void __launch_bounds__(256)
+ulv_factor_kernel_ff(UlvCtx cx, const int32_t* __restrict__ level_nodes, int count, double* scratch, int64_t scratch_stride) {
+  const Team tm{(int)threadIdx.x, (int)blockDim.x};
+  double* s = scratch + (int64_t)blockIdx.x * scratch_stride;
+  for (int i = blockIdx.x; i < count; i += gridDim.x) {
+    ulv_factor_node<true>(tm, cx, level_nodes[i], s);
     __syncthreads();
   }
 }

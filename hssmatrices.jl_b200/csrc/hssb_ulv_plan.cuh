@@ -298,7 +298,10 @@ static void ulv_factor_host(hssb_matrix* H) {
   UlvCtx cx{H->ulv.data(), H->pool_host.data(), H->ulv_pool_host.data(), red.data(), H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW};
   const Team tm{0, 1};
   for (auto& level : ulv_levels(H))
-    for (int32_t node : level) ulv_factor_node(tm, cx, node, scratch.data());
+    for (int32_t node : level) {
+      if (H->ulv_ff) ulv_factor_node<true>(tm, cx, node, scratch.data());
+      else ulv_factor_node<false>(tm, cx, node, scratch.data());
+    }
   H->ulv_factored = true;
 }
 
@@ -338,7 +341,8 @@ static int ulv_factor_device(hssb_matrix* H) {
     for (auto& l : levels) {
       if (!l.empty()) {
         const int grid = (int)std::min<size_t>(l.size(), (size_t)ctas);
-        ulv_factor_kernel<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, stride);
+        if (H->ulv_ff) ulv_factor_kernel_ff<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, stride);
+        else ulv_factor_kernel<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, stride);
         H->launches++;
       }
       at += l.size();
