@@ -3,6 +3,8 @@ include/hssb200.h declares (no compute calls)."""
 import os
 import re
 
+import pytest
+
 
 def test_header_symbols_exported(hb):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -33,3 +35,21 @@ def test_library_is_sm100a_with_fp64_tensor_ops(hb):
     assert "sm_100a" in out
     sass = subprocess.run(["cuobjdump", "-sass", hb.LIB_PATH], capture_output=True, text=True).stdout
     assert "DMMA" in sass
+
+
+def test_plain_c_client_compiles_and_runs(hb, tmp_path):
+    """include/hssb200.h is valid C99 and the library links into a plain C program (the drop-in boundary is a
+    C ABI, not a C++ or torch interface); host-only calls, no GPU needed."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = str(tmp_path / "c_abi_smoke")
+    libdir = os.path.dirname(hb.LIB_PATH)
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-I", os.path.join(root, "include"),
+                           os.path.join(root, "tests", "c_abi_smoke.c"), "-o", exe, "-L", libdir, "-lhssb200",
+                           "-Wl,-rpath," + libdir])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, (out.returncode, out.stdout, out.stderr)
+    assert "C_ABI_OK" in out.stdout
