@@ -23,6 +23,30 @@ int main(void) {
   if (hssb_matmul(h, 2047, 2048, 1, x, 2048, y, 2048, 1.0, 0.0) != HSSB_ERR_DIM) return 9;      /* DimensionMismatch */
   if (strstr(hssb_last_error(), "DimensionMismatch") == NULL) return 10;
   if (hssb_destroy(h) != HSSB_OK) return 11;
+  /* the packer front end from C: a 2-leaf tree (3 x 3 and 2 x 2 leaves, rank 1), post-order registration */
+  {
+    hssb_builder* b = NULL;
+    const double D1[9] = {1, 2, 3, 4, 5, 6, 7, 8, 10}, U1[3] = {1, 0, -1}, V1[3] = {2, 1, 0};
+    const double D2[4] = {3, 1, 1, 2}, U2[2] = {1, 1}, V2[2] = {0.5, -0.5};
+    const double B12[1] = {0.25}, B21[1] = {-0.75};
+    double back[9];
+    hssb_node_t nd;
+    int64_t l, r, root;
+    if (hssb_builder_create(&b) != HSSB_OK) return 12;
+    l = hssb_builder_add_leaf(b, 3, 3, 1, 1, D1, 3, U1, 3, V1, 3);
+    r = hssb_builder_add_leaf(b, 2, 2, 1, 1, D2, 2, U2, 2, V2, 2);
+    root = hssb_builder_add_branch(b, l, r, 0, 0, B12, 1, B21, 1, NULL, 1, NULL, 1, NULL, 1, NULL, 1);
+    if (l < 0 || r < 0 || root < 0) { fprintf(stderr, "%s\n", hssb_last_error()); return 13; }
+    if (hssb_builder_add_leaf(b, 3, 3, 1, 1, D1, 2, U1, 3, V1, 3) != HSSB_ERR_DIM) return 14;   /* ld < rows */
+    if (hssb_plan_only(b, root, 0, 1, &h) != HSSB_OK) { fprintf(stderr, "%s\n", hssb_last_error()); return 15; }
+    hssb_builder_destroy(b);
+    if (hssb_info(h, &info) != HSSB_OK || info.m != 5 || info.n != 5 || info.n_leaves != 2 || info.n_nodes != 3) return 16;
+    if (hssb_node_info(h, 0, &nd) != HSSB_OK || nd.is_leaf || nd.left != 1 || nd.right != 2) return 17;
+    if (hssb_get_block(h, 1, 0, back, 9) != HSSB_OK || memcmp(back, D1, sizeof(D1)) != 0) return 18;   /* D of the left leaf */
+    if (hssb_get_block(h, 0, 3, back, 9) != HSSB_OK || back[0] != 0.25) return 19;                       /* B12 of the root */
+    if (hssb_ulv_info(h, &ui) != HSSB_OK || ui.supported != 1) return 20;
+    if (hssb_destroy(h) != HSSB_OK) return 21;
+  }
   printf("C_ABI_OK\n");
   return 0;
 }
