@@ -171,7 +171,7 @@ def main():
     ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--variant", default="default", help="comma-separated switches: generic, nograph, nccl, adjoint (time Y = A' X), nosolve (skip the ULV solver extra)")
+    ap.add_argument("--variant", default="default", help="comma-separated switches: generic, nograph, nccl, adjoint (time Y = A' X), nosolve (skip the ULV solver extra), ulvfast (experimental solve plan on the fixed-shape kernels)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     cfg = dict(CONFIGS[args.config])
@@ -310,6 +310,8 @@ def main():
     solve = None
     if N == 1 and args.config == "c3" and not adjoint and "nosolve" not in variants:
         try:
+            if "ulvfast" in variants:   # experimental: fixed-shape kernels on the solve plan (HSSB_OPT_ULV_FAST)
+                P.set_option(hb.OPT_ULV_FAST, 1)
             ui = P.ulv_info
             torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -335,6 +337,7 @@ def main():
             solve = {"what": "Z = A \\ X (hssb_solve_dev, ULV factors resident, device time per call)", "ms_per_solve": ms_solve,
                      "gflops": fl_s / ms_solve * 1e-6, "flops": fl_s, "algorithmic_bytes": by_s, "hbm_gbs": by_s / ms_solve * 1e-6,
                      "factor_ms_once": t_factor * 1e3, "factor_pool_gb": ui.pool_bytes * 1e-9,
+                     "fast_form": P.get_option(hb.OPT_ULV_FAST) == 2,
                      "relative_residual": resid, "steps": steps_s,
                      "note": "||A Z - X|| / ||X|| with A Z from the product path; the synthetic matrix is ill conditioned "
                              "(cond ~ 1e7), the scale-free backward error ||A Z - X|| / (||A||_2 ||Z||) is asserted <= 1e-12 in "
