@@ -118,6 +118,7 @@ SIGNATURES = {
     "hssb_debug_phase": (C.c_int, [_P, _i64, C.POINTER(_PhaseT)]),
     "hssb_debug_pool": (C.c_int, [_P, _P, _i64]),
     "hssb_debug_pool_t": (C.c_int, [_P, _P, _i64]),
+    "hssb_debug_tree_trace": (C.c_int, [_P, _i64, _P, C.c_int]),
     "hssb_ulv_factor": (C.c_int, [_P]),
     "hssb_solve": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64]),
     "hssb_solve_dev": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64, _P]),
@@ -126,7 +127,7 @@ SIGNATURES = {
     "hssb_debug_ulv_pool": (C.c_int, [_P, _P, _i64]),
 }
 
-OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS, OPT_ADJOINT_TWIN, OPT_ULV_FAST = 1, 2, 4, 5, 6, 7, 8
+OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS, OPT_ADJOINT_TWIN, OPT_ULV_FAST, OPT_TREE_KERNEL = 1, 2, 4, 5, 6, 7, 8, 9
 PHASE_NAMES = ("leaf_up", "merge", "exchange", "translate", "leaf_down", "exchange_ack")
 KIND_NAMES = ("D", "U", "V", "B12", "B21", "R", "W")
 
@@ -649,6 +650,12 @@ class PackedHss:
         raw = b"".join(blobs)
         buf = (C.c_char * len(raw)).from_buffer_copy(raw)
         _check(lib().hssb_xchg_import(self._h, buf, len(blobs)))
+
+    def tree_trace(self, nrhs):
+        """Microseconds per step (level / exchange) of the persistent tree kernel launched alone (diagnostics)."""
+        buf = np.zeros(256)
+        n = _check(lib().hssb_debug_tree_trace(self._h, nrhs, _ptr(buf), buf.size))
+        return buf[:n].tolist()
 
     # plan export (tests) -------------------------------------------------------
     def debug_pool_t(self):

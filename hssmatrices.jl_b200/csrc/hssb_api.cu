@@ -947,6 +947,10 @@ static XchgParams xchg_params(const hssb_matrix* H, const CallParams& cp) {
   return q;
 }
 
+}  // namespace hssb
+#include "hssb_tree.cuh"
+namespace hssb {
+
 // ------------------------------------------------------------------ launch ---
 static int launch_generic(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
   if (ph.ntasks == 0) return HSSB_OK;
@@ -975,9 +979,40 @@ static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
     HSSB_CUDA(cudaEventRecord(H->prof_events[0], st));
     H->prof_nrhs = cp.nrhs;
   }
+  // every level between the two leaf kernels in one persistent launch (hssb_tree.cuh)
+  const TreePlan* tp = nullptr;
+  if (cp.trans == 0 && H->tree_kernel && !H->force_generic) {
+    tp = (const TreePlan*)H->tree_plan;  // built by matmul_dev_impl (outside graph capture)
+    if (tp && tp->steps.empty()) tp = nullptr;
+  }
   size_t pi = 0;
   for (const Phase& ph : phases) {
     ++pi;
+    if (tp && (int)pi - 1 >= tp->phase0 && (int)pi - 1 < tp->phase1) {
+      if ((int)pi - 1 > tp->phase0) continue;  // launched with the first covered phase
+      const int ns = (int)tp->steps.size();
+      XchgParams xq;
+      memset(&xq, 0, sizeof(xq));
+      int rc = HSSB_OK;
+      if (tp->xchg_step < 0) {
+        rc = launch_tree(H, tp, 0, ns, cp, xq, st);
+      } else if (H->peer_xchg) {
+        rc = launch_tree(H, tp, 0, ns, cp, xchg_params(H, cp), st);  // exchange + acknowledgement inside the kernel
+      } else {
+        // NCCL all-gather between two launches; the acknowledgement step is a no-op (no peer flags)
+        if (!H->nccl_comm) HSSB_FAIL(HSSB_ERR_STATE, "sharded matrix: call hssb_comm_init (or hssb_xchg_import) before hssb_matmul");
+        rc = launch_tree(H, tp, 0, tp->xchg_step, cp, xq, st);
+        if (rc) return rc;
+        double* buf = cp.Z + H->xchg_zoff * (int64_t)cp.nrhs;
+        const size_t count = (size_t)H->xchg_slot_rows * (size_t)cp.nrhs;
+        HSSB_NCCL(g_nccl.AllGather(buf + (size_t)H->shard_rank * count, buf, count, /*ncclDouble*/ 8, H->nccl_comm, st));
+        rc = launch_tree(H, tp, tp->xchg_step + 1, ns, cp, xq, st);
+      }
+      if (rc) return rc;
+      if (prof)  // the covered phases share one launch: its time is reported on the first of them
+        for (int q = tp->phase0; q < tp->phase1; ++q) cudaEventRecord(H->prof_events[(size_t)q + 1], st);
+      continue;
+    }
     struct Rec {
       hssb_matrix* H; cudaStream_t st; size_t i; bool on;
       ~Rec() { if (on) cudaEventRecord(H->prof_events[i], st); }
@@ -1202,6 +1237,7 @@ int hssb_destroy(hssb_matrix* h) {
   if (h->stream) cudaStreamSynchronize(h->stream);
   invalidate_graphs(h);
   free_fast(h);
+  free_tree(h);
   for (auto e : h->prof_events) cudaEventDestroy(e);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   for (int r = 0; r < hssb_matrix::MAX_PEERS; ++r)
@@ -1336,6 +1372,10 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
     rc = prepare_solve(h);
     if (rc) return rc;
     pool = h->ulv_pool_dev;
+  }
+  if (trans == 0 && h->tree_kernel && !h->force_generic) {  // allocates: must happen outside graph capture
+    rc = ensure_tree_plan(h);
+    if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
   CallParams cp;
@@ -1530,6 +1570,7 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
     case HSSB_OPT_DEBUG: h->debug_mode = (int)value; break;
     case HSSB_OPT_PIPELINE_COLS: h->pipeline_cols = value; break;
     case HSSB_OPT_ADJOINT_TWIN: h->adjoint_twin = value != 0; break;
+    case HSSB_OPT_TREE_KERNEL: h->tree_kernel = (int)value; break;
     case HSSB_OPT_ULV_FAST: {
       if (h->ulv_fast_form == (value != 0)) return HSSB_OK;
       h->ulv_fast_form = value != 0;
@@ -1559,6 +1600,7 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
     case HSSB_OPT_PIPELINE_COLS: return h->pipeline_cols;
     case HSSB_OPT_ADJOINT_TWIN: return !h->adjoint_twin ? 0 : (h->pool_t_dev ? 2 : 1);  // 2: built and in use
     case HSSB_OPT_ULV_FAST: return !h->ulv_fast_form ? 0 : (h->ulv_ff ? 2 : 1);          // 2: the plan is in fast form
+    case HSSB_OPT_TREE_KERNEL: return h->tree_kernel;
     default: return -1;
   }
 }
@@ -1623,8 +1665,8 @@ int hssb_xchg_export(hssb_matrix* h, void* out128) {
   if (!h->z_dev) HSSB_FAIL(HSSB_ERR_STATE, "hssb_xchg_export: call hssb_reserve(max_nrhs) first");
   DeviceGuard dg(h->device);
   if (!h->my_flags) {
-    HSSB_CUDA(cudaMalloc(&h->my_flags, 64 * sizeof(unsigned long long)));
-    HSSB_CUDA(cudaMemset(h->my_flags, 0, 64 * sizeof(unsigned long long)));
+    HSSB_CUDA(cudaMalloc(&h->my_flags, XCHG_FLAG_WORDS * sizeof(unsigned long long)));
+    HSSB_CUDA(cudaMemset(h->my_flags, 0, XCHG_FLAG_WORDS * sizeof(unsigned long long)));
     HSSB_CUDA(cudaDeviceSynchronize());
   }
   cudaIpcMemHandle_t hz, hf;
@@ -1821,6 +1863,43 @@ int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* o) {
   o->top = p.top; o->fast = p.fast; o->transposed = which;
   o->xchg_zoff = h->xchg_zoff; o->xchg_slot_rows = h->xchg_slot_rows;
   return HSSB_OK;
+}
+
+// Per-step device time of the persistent tree kernel (single shard, diagnostics): launches the tree
+// kernel alone on the current workspace contents with CTA 0 recording its SM clock at every grid
+// barrier.  us_out[j] = microseconds of step j (j-th covered phase of the forward plan).
+int hssb_debug_tree_trace(hssb_matrix* h, int64_t nrhs, double* us_out, int cap) {
+  if (!h || !us_out || nrhs <= 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_tree_trace: bad argument");
+  if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle has no device");
+  if (h->n_shards != 1) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_tree_trace: single-shard handles only");
+  DeviceGuard dg(h->device);
+  int rc = ensure_workspace(h, nrhs);
+  if (rc) return rc;
+  rc = ensure_tree_plan(h);
+  if (rc) return rc;
+  const TreePlan* tp = (const TreePlan*)h->tree_plan;
+  const int ns = (int)tp->steps.size();
+  if (ns == 0) return 0;
+  if (cap < ns) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_tree_trace: need room for %d steps", ns);
+  long long* trace = nullptr;
+  HSSB_CUDA(cudaMalloc(&trace, (size_t)(ns + 1) * sizeof(long long)));
+  CallParams cp;
+  memset(&cp, 0, sizeof(cp));
+  cp.pool = h->pool_dev; cp.Z = h->z_dev; cp.F = h->f_dev; cp.nrhs = (int32_t)nrhs; cp.alpha = 1.0;
+  XchgParams xq;
+  memset(&xq, 0, sizeof(xq));
+  std::vector<long long> t((size_t)ns + 1);
+  for (int rep = 0; rep < 3 && !rc; ++rep) {  // the last repetition is reported (warm instruction cache / L2)
+    rc = launch_tree(h, tp, 0, ns, cp, xq, h->stream, trace);
+    if (!rc && cudaStreamSynchronize(h->stream) != cudaSuccess) { set_error("hssb_debug_tree_trace: %s", cudaGetErrorString(cudaGetLastError())); rc = HSSB_ERR_CUDA; }
+  }
+  if (!rc && cudaMemcpy(t.data(), trace, t.size() * sizeof(long long), cudaMemcpyDeviceToHost) != cudaSuccess) rc = HSSB_ERR_CUDA;
+  cudaFree(trace);
+  if (rc) return rc;
+  int khz = 1965000;
+  cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
+  for (int j = 0; j < ns; ++j) us_out[j] = (double)(t[(size_t)j + 1] - t[(size_t)j]) / (khz * 1e-3);
+  return ns;
 }
 
 int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len) {

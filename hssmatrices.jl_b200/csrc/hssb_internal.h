@@ -228,4 +228,8 @@ struct hssb_matrix {
   std::vector<GraphSlot> graphs;
   // fixed-shape kernel state (hssb_fast.cuh)
   void* fast_state = nullptr;
+  // persistent tree kernel (hssb_tree.cuh): 1 = all merge / translate levels (and the peer exchange) in one
+  // cooperative launch, 0 = one launch per level, 2 = as 1 without the cooperative attribute (diagnostics)
+  int tree_kernel = 1;
+  void* tree_plan = nullptr;
 };

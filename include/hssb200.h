@@ -207,6 +207,10 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
                                     leaf phases, square merges and top-down steps.  Rebuilds the solve plan and drops existing factors.
                                     hssb_get_option returns 2 when the plan is in fast form.  Plan and factorisation are covered by the
                                     CPU tests; the kernels' use on this plan has not been run on a GPU yet.                            */
+#define HSSB_OPT_TREE_KERNEL 9   /* 1 (default): on uniform trees every merge / translate level between the two leaf kernels (and, on
+                                    sharded handles with the NVLink exchange, the exchange itself) runs inside ONE persistent cooperative
+                                    kernel with grid barriers (csrc/hssb_tree.cuh) instead of one launch per level; 0: one launch per
+                                    level (the round-1 schedule, kept as a cross-check); 2: as 1 without the cooperative-launch attribute */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
@@ -274,6 +278,9 @@ int hssb_debug_counts(const hssb_matrix* h, int64_t* n_tasks, int64_t* n_phases,
 int hssb_debug_task(const hssb_matrix* h, int64_t i, hssb_task_t* out);
 int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* out);
 int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len);
+/* Diagnostics: per-step microseconds of the persistent tree kernel (HSSB_OPT_TREE_KERNEL) launched alone on the
+ * current workspace contents; returns the number of steps written (<= cap) or a negative status.               */
+int hssb_debug_tree_trace(hssb_matrix* h, int64_t nrhs, double* us_out, int cap);
 int hssb_debug_pool_t(const hssb_matrix* h, double* out, int64_t len); /* image of the adjoint twin pool */
 /* ULV: factorise a plan-only handle on the host with the device's node routine (single-thread team),
  * and read the factor pool (either kind of handle) for the numpy plan interpreter.                   */
