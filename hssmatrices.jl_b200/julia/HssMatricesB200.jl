@@ -15,7 +15,6 @@ using HssMatrices: HssMatrix, isleaf, gensize
 using LinearAlgebra
 import Base: *, \
 import LinearAlgebra: mul!
-import HssMatrices: ulvfactsolve
 
 const libhssb = get(ENV, "HSSB200_LIB", joinpath(@__DIR__, "..", "lib", "libhssb200.so"))
 
@@ -138,7 +137,7 @@ end
 # hssA \ B (src/hssmatrix.jl:234) = ulvfactsolve (src/ulvfactor.jl:10-19).  The reference factorises and
 # solves in one pass on every call; the library factorises once per packed handle (hssb_ulv_factor, on
 # the device) and every further solve only applies the stored factors.
-function ulvfactsolve(p::PackedHss, B::StridedMatrix{Float64})
+function HssMatrices.ulvfactsolve(p::PackedHss, B::StridedMatrix{Float64})
   size(p, 1) == size(B, 1) || throw(DimensionMismatch("First dimension of B does not match first dimension of A."))
   stride(B, 1) == 1 || throw(ArgumentError("B needs unit stride in the first dimension"))
   Z = Matrix{Float64}(undef, size(p, 2), size(B, 2))
@@ -148,24 +147,68 @@ function ulvfactsolve(p::PackedHss, B::StridedMatrix{Float64})
   end
   return Z
 end
-\(p::PackedHss, B::StridedMatrix{Float64}) = ulvfactsolve(p, B)
-\(p::PackedHss, b::StridedVector{Float64}) = reshape(ulvfactsolve(p, reshape(b, length(b), 1)), length(b))
+\(p::PackedHss, B::StridedMatrix{Float64}) = HssMatrices.ulvfactsolve(p, B)
+\(p::PackedHss, b::StridedVector{Float64}) = reshape(HssMatrices.ulvfactsolve(p, reshape(b, length(b), 1)), length(b))
 """Factorise ahead of time (otherwise the first `\\` does it)."""
 ulvfactor!(p::PackedHss) = (check(ccall((:hssb_ulv_factor, libhssb), Cint, (Ptr{Cvoid},), p.handle)); p)
 
 # ---- drop-in methods on HssMatrix{Float64} ---------------------------------------------------
-# HssMatrix is mutable (recompress!, prune_leaves!, field assignment as in test/runtests.jl:75), so
-# the device copy is cached per object identity and must be dropped by hand after a mutation.
-const CACHE = IdDict{HssMatrix{Float64}, PackedHss}()
-packed(hssA::HssMatrix{Float64}) = get!(() -> pack(hssA), CACHE, hssA)
-"""Forget the device copy of `hssA` (call after mutating it)."""
-invalidate!(hssA::HssMatrix{Float64}) = (delete!(CACHE, hssA); nothing)
+# HssMatrix is mutable (recompress!, prune_leaves!, field assignment as in test/runtests.jl:75), so a
+# device copy cached per object can go stale.  The cache therefore
+#   * holds its keys WEAKLY (WeakKeyDict): an HssMatrix the caller drops is collected as usual, and the
+#     finalizer of its PackedHss then frees the device pool;
+#   * stores a fingerprint of the generator tree next to the handle (per generator: data pointer, size
+#     and three sampled entries, O(#nodes), no pass over the data) and re-packs when it changed.  This
+#     catches field assignment, recompress!, prune_leaves! and orthonormalize_generators! (they replace
+#     or resize the generator arrays); an in-place edit of single entries that misses the three samples
+#     needs invalidate!(hssA).
+# Only `*` and `mul!` (src/matmul.jl:13-28) are overridden for HssMatrix.  The solver entries
+# (`\`, ulvfactsolve) are deliberately NOT: the reference routes `/(A, hssB)` through
+# `ulvfactsolve(hssB', ...)` on a temporary adjoint (src/hssmatrix.jl:236), which would pack, factorise
+# and cache a device copy of an object the caller never sees.  Use `pack(hssA) \ B` for the GPU solver.
+struct CacheEntry
+  packed::PackedHss
+  fingerprint::UInt64
+end
+const CACHE = WeakKeyDict{HssMatrix{Float64}, CacheEntry}()
+const CACHE_LOCK = ReentrantLock()
+
+@inline function fp_block(h::UInt64, A::Matrix{Float64})
+  h = hash(UInt(pointer(A)), hash(size(A), h))
+  n = length(A)
+  n == 0 && return h
+  @inbounds return hash(A[1], hash(A[(n + 1) >> 1], hash(A[n], h)))
+end
+function fingerprint(hssA::HssMatrix{Float64}, isroot::Bool=true, h::UInt64=UInt64(0x48535342))
+  if isleaf(hssA)
+    h = fp_block(h, hssA.D)
+    isroot || (h = fp_block(fp_block(h, hssA.U), hssA.V))
+    return h
+  end
+  h = fingerprint(hssA.A11, false, h)
+  h = fingerprint(hssA.A22, false, h)
+  h = fp_block(fp_block(h, hssA.B12), hssA.B21)
+  isroot || (h = fp_block(fp_block(fp_block(fp_block(h, hssA.R1), hssA.W1), hssA.R2), hssA.W2))
+  return h
+end
+
+function packed(hssA::HssMatrix{Float64})
+  fp = fingerprint(hssA)
+  lock(CACHE_LOCK) do
+    e = get(CACHE, hssA, nothing)
+    if e === nothing || e.fingerprint != fp
+      e = CacheEntry(pack(hssA), fp)   # the replaced PackedHss is freed by its finalizer
+      CACHE[hssA] = e
+    end
+    return e.packed
+  end
+end
+"""Forget the device copy of `hssA` (only needed after editing single entries of a generator in place)."""
+invalidate!(hssA::HssMatrix{Float64}) = (lock(() -> delete!(CACHE, hssA), CACHE_LOCK); nothing)
 
 mul!(C::StridedMatrix{Float64}, hssA::HssMatrix{Float64}, B::StridedMatrix{Float64}, α::Real, β::Real) = mul!(C, packed(hssA), B, α, β)
 *(hssA::HssMatrix{Float64}, B::StridedMatrix{Float64}) = packed(hssA) * B
 *(A::StridedMatrix{Float64}, hssB::HssMatrix{Float64}) = A * packed(hssB)
-\(hssA::HssMatrix{Float64}, B::Matrix{Float64}) = packed(hssA) \ B                      # src/hssmatrix.jl:234
-ulvfactsolve(hssA::HssMatrix{Float64}, B::Matrix{Float64}) = ulvfactsolve(packed(hssA), B)  # src/ulvfactor.jl:10
 
 export pack, PackedHss, invalidate!, ulvfactor!
 
