@@ -526,12 +526,16 @@ def main():
         xp = np.array(xs, order="F", copy=True)
         yp = np.empty((rows, k), order="F")
         t_page = e2e_leg(xp, yp, steps_e)
+        staged = int(P.get_option(hb.OPT_LAST_BOUNCE))
         chk_p = float(np.linalg.norm(yp[:, 0] - ys[:, 0]) / max(np.linalg.norm(ys[:, 0]), 1e-300))
         e2e = {"value": flops_all / t_pin * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * rows * k,
                "d2h_bytes_per_step": 8 * rows * k, "ms_per_step": t_pin * 1e3, "steps": steps_e,
                "host_memory": "pinned", "matches_device_path": chk <= 1e-12,
                "pageable": {"value": flops_all / t_page * 1e-9, "unit": "GFLOP/s", "ms_per_step": t_page * 1e3,
                             "host_memory": "pageable (numpy arrays, as a Julia Matrix would be)",
+                            "staging": ("library ring of pinned 2 MiB slots + worker threads (csrc/hssb_hostpipe.h)"
+                                        if staged == 3 else f"driver (cudaMemcpy2DAsync on the caller's pointer), ring bits {staged}"),
+                            "host_threads_per_direction": int(os.environ.get("HSSB_HOST_THREADS", min(8, max(2, (os.cpu_count() or 8) // 2)))),
                             "vs_pinned": t_page / t_pin, "matches_pinned": chk_p <= 1e-12}}
         del Xh, Yh, xp, yp
 

@@ -949,6 +949,7 @@ static XchgParams xchg_params(const hssb_matrix* H, const CallParams& cp) {
 
 }  // namespace hssb
 #include "hssb_tree.cuh"
+#include "hssb_hostpipe.h"
 namespace hssb {
 
 // ------------------------------------------------------------------ launch ---
@@ -1254,6 +1255,7 @@ int hssb_destroy(hssb_matrix* h) {
   cudaFree(h->f_dev);
   cudaFree(h->x_stage);
   cudaFree(h->y_stage);
+  delete (Bounce*)h->bounce;
   if (h->copy_in) {
     cudaStreamDestroy(h->copy_in);
     cudaStreamDestroy(h->copy_out);
@@ -1445,30 +1447,82 @@ static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t r
   else if (nrhs >= 16 && rows_eff * nrhs * 8 >= ((int64_t)64 << 20)) cb = std::max<int64_t>(8, ((nrhs + 7) / 8 + 7) / 8 * 8);  // ~8 blocks: measured best on PCIe Gen5 (tools/e2e_blocks.py)
   int64_t nblk = (nrhs + cb - 1) / cb;
   if (nblk > hssb_matrix::MAX_BLOCKS) { cb = (nrhs + hssb_matrix::MAX_BLOCKS - 1) / hssb_matrix::MAX_BLOCKS; nblk = (nrhs + cb - 1) / cb; }
+  // Pageable caller memory (an ordinary Julia Matrix) goes through the library's pinned slot rings and
+  // worker threads (hssb_hostpipe.h); pinned / registered memory is handed to the copy engines directly.
+  // Small calls are not worth the thread hand-offs.
+  const bool big = (rows_x + rows_y) * nrhs * 8 >= ((int64_t)16 << 20);
+  const bool bounce_in = rows_x > 0 && h->host_bounce && (h->host_bounce == 2 || (big && host_ptr_pageable(X)));
+  const bool bounce_out = h->host_bounce && (h->host_bounce == 2 || (big && host_ptr_pageable(Y)));
+  Bounce* bn = (Bounce*)h->bounce;
+  if ((bounce_in || bounce_out) && !bn) {
+    bn = new (std::nothrow) Bounce();
+    if (!bn) HSSB_FAIL(HSSB_ERR_ALLOC, "hssb_matmul: out of memory");
+    if (int rc = bn->init(h->device)) { delete bn; return rc; }
+    h->bounce = bn;
+  }
+  h->last_bounce = (bounce_in ? 1 : 0) | (bounce_out ? 2 : 0);
+  std::vector<Latch> in_latch((size_t)(bounce_in ? nblk : 0));
+  Latch out_latch;
+  auto drain = [&]() {  // nothing may still reference the caller's memory or this frame when we return
+    for (auto& l : in_latch) l.wait();
+    out_latch.wait();
+    cudaStreamSynchronize(h->copy_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_out);
+  };
   // copies of this call must not overtake the previous call's use of the staging buffers
   HSSB_CUDA(cudaEventRecord(h->ev_done[0], h->stream));
   HSSB_CUDA(cudaStreamWaitEvent(h->copy_in, h->ev_done[0], 0));
   for (int64_t j = 0; j < nblk; ++j) {
     const int64_t c0 = j * cb, nc = std::min(cb, nrhs - c0);
+    if (bounce_in) {
+      Latch* l = &in_latch[(size_t)j];
+      Bounce::for_pieces(rows_x, nc, ldx, sx, [&](size_t oh, size_t od, size_t bytes) {
+        bn->submit_in((const char*)(X + c0 * ldx) + oh, (char*)(h->x_stage + c0 * sx) + od, bytes, h->copy_in, l);
+      });
+      if (beta != 0.0)
+        Bounce::for_pieces(rows_y, nc, ldy, sy, [&](size_t oh, size_t od, size_t bytes) {
+          bn->submit_in((const char*)(Y + c0 * ldy) + oh, (char*)(h->y_stage + c0 * sy) + od, bytes, h->copy_in, l);
+        });
+      continue;  // the block's event is recorded once its pieces have been queued (below)
+    }
+    cudaError_t e = cudaSuccess;
     if (rows_x > 0)
-      HSSB_CUDA(cudaMemcpy2DAsync(h->x_stage + c0 * sx, (size_t)sx * 8, X + c0 * ldx, (size_t)ldx * 8, (size_t)rows_x * 8,
-                                  (size_t)nc, cudaMemcpyHostToDevice, h->copy_in));
-    if (beta != 0.0)
-      HSSB_CUDA(cudaMemcpy2DAsync(h->y_stage + c0 * sy, (size_t)sy * 8, Y + c0 * ldy, (size_t)ldy * 8, (size_t)rows_y * 8,
-                                  (size_t)nc, cudaMemcpyHostToDevice, h->copy_in));
-    HSSB_CUDA(cudaEventRecord(h->ev_in[j], h->copy_in));
+      e = cudaMemcpy2DAsync(h->x_stage + c0 * sx, (size_t)sx * 8, X + c0 * ldx, (size_t)ldx * 8, (size_t)rows_x * 8, (size_t)nc,
+                            cudaMemcpyHostToDevice, h->copy_in);
+    if (e == cudaSuccess && beta != 0.0)
+      e = cudaMemcpy2DAsync(h->y_stage + c0 * sy, (size_t)sy * 8, Y + c0 * ldy, (size_t)ldy * 8, (size_t)rows_y * 8, (size_t)nc,
+                            cudaMemcpyHostToDevice, h->copy_in);
+    if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[j], h->copy_in);
+    if (e != cudaSuccess) { drain(); HSSB_CUDA(e); }
   }
   for (int64_t j = 0; j < nblk; ++j) {
     const int64_t c0 = j * cb, nc = std::min(cb, nrhs - c0);
-    HSSB_CUDA(cudaStreamWaitEvent(h->stream, h->ev_in[j], 0));
+    cudaError_t e = cudaSuccess;
+    if (bounce_in) {
+      e = in_latch[(size_t)j].wait();  // every piece of the block is queued on copy_in
+      if (e == cudaSuccess) e = cudaEventRecord(h->ev_in[j], h->copy_in);
+    }
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->stream, h->ev_in[j], 0);
+    if (e != cudaSuccess) { drain(); HSSB_CUDA(e); }
     h->in_host_call = true;
     int rc = matmul_dev_impl(h, trans, rows_y, rows_x, nc, h->x_stage + c0 * sx, sx, h->y_stage + c0 * sy, sy, alpha, beta, h->stream);
     h->in_host_call = false;
-    if (rc) { cudaStreamSynchronize(h->copy_in); cudaStreamSynchronize(h->stream); cudaStreamSynchronize(h->copy_out); return rc; }
-    HSSB_CUDA(cudaEventRecord(h->ev_done[j], h->stream));
-    HSSB_CUDA(cudaStreamWaitEvent(h->copy_out, h->ev_done[j], 0));
-    HSSB_CUDA(cudaMemcpy2DAsync(Y + c0 * ldy, (size_t)ldy * 8, h->y_stage + c0 * sy, (size_t)sy * 8, (size_t)rows_y * 8,
-                                (size_t)nc, cudaMemcpyDeviceToHost, h->copy_out));
+    if (rc) { drain(); return rc; }
+    e = cudaEventRecord(h->ev_done[j], h->stream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(h->copy_out, h->ev_done[j], 0);
+    if (e == cudaSuccess) {
+      if (bounce_out)
+        Bounce::for_pieces(rows_y, nc, ldy, sy, [&](size_t oh, size_t od, size_t bytes) {
+          bn->submit_out((const char*)(h->y_stage + c0 * sy) + od, (char*)(Y + c0 * ldy) + oh, bytes, h->copy_out, &out_latch);
+        });
+      else
+        e = cudaMemcpy2DAsync(Y + c0 * ldy, (size_t)ldy * 8, h->y_stage + c0 * sy, (size_t)sy * 8, (size_t)rows_y * 8, (size_t)nc,
+                              cudaMemcpyDeviceToHost, h->copy_out);
+    }
+    if (e != cudaSuccess) { drain(); HSSB_CUDA(e); }
+  }
+  {
+    const cudaError_t e = out_latch.wait();
+    if (e != cudaSuccess) { drain(); HSSB_CUDA(e); }
   }
   HSSB_CUDA(cudaStreamSynchronize(h->copy_out));
   HSSB_CUDA(cudaStreamSynchronize(h->stream));
@@ -1571,6 +1625,10 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
     case HSSB_OPT_PIPELINE_COLS: h->pipeline_cols = value; break;
     case HSSB_OPT_ADJOINT_TWIN: h->adjoint_twin = value != 0; break;
     case HSSB_OPT_TREE_KERNEL: h->tree_kernel = (int)value; break;
+    case HSSB_OPT_HOST_BOUNCE:
+      if (value < 0 || value > 2) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_HOST_BOUNCE: 0, 1 or 2");
+      h->host_bounce = (int)value;
+      return HSSB_OK;
     case HSSB_OPT_ULV_FAST: {
       if (h->ulv_fast_form == (value != 0)) return HSSB_OK;
       h->ulv_fast_form = value != 0;
@@ -1601,6 +1659,8 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
     case HSSB_OPT_ADJOINT_TWIN: return !h->adjoint_twin ? 0 : (h->pool_t_dev ? 2 : 1);  // 2: built and in use
     case HSSB_OPT_ULV_FAST: return !h->ulv_fast_form ? 0 : (h->ulv_ff ? 2 : 1);          // 2: the plan is in fast form
     case HSSB_OPT_TREE_KERNEL: return h->tree_kernel;
+    case HSSB_OPT_HOST_BOUNCE: return h->host_bounce;
+    case HSSB_OPT_LAST_BOUNCE: return h->last_bounce;
     default: return -1;
   }
 }

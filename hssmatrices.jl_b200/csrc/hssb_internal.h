@@ -190,6 +190,10 @@ struct hssb_matrix {
   cudaStream_t copy_in = nullptr, copy_out = nullptr;
   cudaEvent_t ev_in[MAX_BLOCKS] = {}, ev_done[MAX_BLOCKS] = {};
   int64_t pipeline_cols = 0;  // 0 = automatic
+  // pageable caller memory: pinned slot rings + worker threads (hssb_hostpipe.h).  0 never, 1 automatic, 2 always
+  int host_bounce = 1;
+  int last_bounce = 0;  // what the last host call did: bit 0 = X went through the ring, bit 1 = Y
+  void* bounce = nullptr;
   int64_t launches = 0;
   // global / local shape
   int64_t m = 0, n = 0, local_m = 0, local_n = 0, local_row0 = 0, local_col0 = 0;

@@ -211,6 +211,12 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
                                     sharded handles with the NVLink exchange, the exchange itself) runs inside ONE persistent cooperative
                                     kernel with grid barriers (csrc/hssb_tree.cuh) instead of one launch per level; 0: one launch per
                                     level (the round-1 schedule, kept as a cross-check); 2: as 1 without the cooperative-launch attribute */
+#define HSSB_OPT_HOST_BOUNCE 10  /* host entry, PAGEABLE caller memory (an ordinary Julia Matrix, matmul.jl:13): 1 (default) = calls of
+                                    16 MiB and more whose X / Y pointer is not pinned or registered are staged by the library through
+                                    rings of pinned 2 MiB slots filled / drained by worker threads (HSSB_HOST_THREADS per direction,
+                                    default min(8, cores / 2)), so that staging overlaps the DMA and the kernels; 0 = hand every
+                                    pointer to cudaMemcpy2DAsync as it is; 2 = always stage (tests)                                 */
+#define HSSB_OPT_LAST_BOUNCE 11  /* read-only: what the last host call staged through the rings (bit 0: X, bit 1: Y)                */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */

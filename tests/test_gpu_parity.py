@@ -341,3 +341,57 @@ def test_two_gpu_sharded(gpu, oracle):
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "SHARDED_OK" in out.stdout
+
+
+def test_pageable_host_memory_ring(gpu, oracle):
+    """hssb_matmul on pageable caller memory (what Julia's `similar(B, ...)`, matmul.jl:13, hands over) goes
+    through the library's pinned slot rings and worker threads (csrc/hssb_hostpipe.h).  HSSB_OPT_HOST_BOUNCE = 2
+    forces that path for a small matrix: strided X / Y (leading dimension > rows: column-by-column pieces),
+    dense ones (whole-panel pieces), beta != 0 (Y travels both ways) -- identical to the direct path."""
+    rng = np.random.default_rng(77)
+    n, k = 777, 9
+    cl = oracle.bisection_cluster(n, 50)
+    h = oracle.random_hss(cl, cl, rng, 1, 9)
+    tree = to_product_tree(gpu, h)
+    P = tree.repack()
+    lib = gpu.lib()
+    Xbig = np.asfortranarray(rng.standard_normal((n + 13, k)))
+    Ybig = np.asfortranarray(rng.standard_normal((n + 5, k)))
+    ref = oracle.mul(Ybig[:n].copy(), h, Xbig[:n], 0.7, -1.3)
+    outs = []
+    for mode in (0, 2):
+        P.set_option(gpu.OPT_HOST_BOUNCE, mode)
+        Yc = Ybig.copy(order="F")
+        rc = lib.hssb_matmul(P._h, n, n, k, Xbig.ctypes.data, n + 13, Yc.ctypes.data, n + 5, 0.7, -1.3)
+        assert rc == 0, lib.hssb_last_error()
+        assert P.get_option(gpu.OPT_LAST_BOUNCE) == (3 if mode else 0)
+        assert relerr(Yc[:n], ref) <= TOL
+        assert np.array_equal(Yc[n:], Ybig[n:])      # rows beyond the matrix are not touched
+        outs.append(Yc)
+    assert np.array_equal(outs[0], outs[1])
+    Xd = np.asfortranarray(Xbig[:n])
+    Yd = np.full((n, k), np.nan, order="F")
+    P.mul_(Yd, Xd)                                    # dense panels, beta == 0 never reads Y
+    assert P.get_option(gpu.OPT_LAST_BOUNCE) == 3 and relerr(Yd, oracle.matmul(h, Xd)) <= TOL
+    P.set_option(gpu.OPT_HOST_BOUNCE, 1)
+    P.mul_(Yd, Xd)                                    # automatic: a call this small is not staged
+    assert P.get_option(gpu.OPT_LAST_BOUNCE) == 0
+    P.close()
+
+
+def test_pageable_large_call_is_staged(gpu, oracle):
+    """A config-3-sized call (64 MiB and more) on numpy memory takes the ring by default and matches the
+    pinned-memory result bit for bit."""
+    import torch
+    n, ls, r, k, seed = 2 ** 17, 128, 32, 32, 5
+    with gpu.synthetic(n, ls, r, seed) as P:
+        X = oracle.synth_x(seed, n, k)
+        Yp = np.empty((n, k), order="F")
+        P.mul_(Yp, X)
+        assert P.get_option(gpu.OPT_LAST_BOUNCE) == 3
+        Xh = torch.empty((k, n), dtype=torch.float64).pin_memory()
+        Yh = torch.empty((k, n), dtype=torch.float64).pin_memory()
+        Xh.numpy().T[:] = X
+        P.mul_(Yh.numpy().T, Xh.numpy().T)
+        assert P.get_option(gpu.OPT_LAST_BOUNCE) == 0
+        assert np.array_equal(Yh.numpy().T, Yp)
