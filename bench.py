@@ -306,8 +306,8 @@ class Run:
         if "generic" in variants:
             P.set_option(hb.OPT_FORCE_GENERIC, 1)
         P.set_option(hb.OPT_USE_GRAPH, 0 if "nograph" in variants else 1)
-        if "notree" in variants:     # round-1 schedule: one launch per tree level
-            P.set_option(hb.OPT_TREE_KERNEL, 0)
+        if "tree" in variants:       # all merge / translate levels in one persistent cooperative launch (opt-in)
+            P.set_option(hb.OPT_TREE_KERNEL, 1)
         self.P = P
         self.rows = P.info.local_n
         self.row0 = P.info.local_col0

@@ -1625,6 +1625,10 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
     case HSSB_OPT_PIPELINE_COLS: h->pipeline_cols = value; break;
     case HSSB_OPT_ADJOINT_TWIN: h->adjoint_twin = value != 0; break;
     case HSSB_OPT_TREE_KERNEL: h->tree_kernel = (int)value; break;
+    case HSSB_OPT_LEAF_KERNEL:
+      if (value < 1 || value > 3) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_LEAF_KERNEL: 1, 2 or 3");
+      h->leaf_kernel = (int)value;
+      break;
     case HSSB_OPT_HOST_BOUNCE:
       if (value < 0 || value > 2) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_HOST_BOUNCE: 0, 1 or 2");
       h->host_bounce = (int)value;
@@ -1660,6 +1664,7 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
     case HSSB_OPT_ULV_FAST: return !h->ulv_fast_form ? 0 : (h->ulv_ff ? 2 : 1);          // 2: the plan is in fast form
     case HSSB_OPT_TREE_KERNEL: return h->tree_kernel;
     case HSSB_OPT_HOST_BOUNCE: return h->host_bounce;
+    case HSSB_OPT_LEAF_KERNEL: return h->leaf_kernel;
     case HSSB_OPT_LAST_BOUNCE: return h->last_bounce;
     default: return -1;
   }

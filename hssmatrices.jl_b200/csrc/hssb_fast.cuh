@@ -75,6 +75,9 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
                : "memory");
 }
 
+// n-index of a DMMA tile -> right-hand side within its 8-column group (see stream_leaf_kernel)
+__device__ __forceinline__ int perm8(int n) { return (0x74216530u >> (4 * n)) & 7; }
+
 // ------------------------------------------------------------- leaf shapes ---
 // Both leaf kernels are one template: a persistent, warp-specialised, streamed-A GEMM
 //     OUT[MO x NT] = [A0 | A1] * [X ; F]           (K = K0 + K1)
@@ -225,6 +228,13 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
   // ~100-cycle mbarrier round trip never sits between two DMMAs of this warp.
   const int gq = lane >> 2, t = lane & 3;
   const int wr = warp % C::WR, wc = warp / C::WR;
+  // Which right-hand side the n-index of a DMMA tile stands for is free: n -> column perm8(n) of the
+  // 8-column group.  With the identity, the half-warp gq = 0..3 reads rows 0..3 of the swizzled X box,
+  // whose 16-byte chunks (c ^ row) collide pairwise (rows 0/1 and 2/3 swap the same two chunks): a
+  // 2-way bank conflict on every B fragment load.  Rows {0,3,5,6} / {1,2,4,7} differ in bits 1-2 (X box:
+  // 8 distinct chunks per half-warp) and in row mod 4 (padded F block, 4*row + t mod 16): conflict free
+  // on both operands.
+  const int pg = perm8(gq);
   double acc[C::TM][C::TN][2];
 #pragma unroll
   for (int i = 0; i < C::TM; ++i)
@@ -255,7 +265,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
     if (XPART) {
       const int qb = kstep0 & 3;  // non-zero only when a chunk is shorter than a 16-row slab (KSTEPS == 2)
 #pragma unroll
-      for (int q = 0; q < 4; ++q) sw[q] = ((((qb + q) & 3) * 2 + (t >> 1)) ^ gq) * 2 + (t & 1);
+      for (int q = 0; q < 4; ++q) sw[q] = ((((qb + q) & 3) * 2 + (t >> 1)) ^ pg) * 2 + (t & 1);
       B += (kstep0 >> 2) * (C::NT * 16);
     }
 #pragma unroll
@@ -291,7 +301,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
     // issue the loads the epilogue needs now; their latency hides behind the whole item
     const int task_i = (first + item) / ntiles, tile = (first + item) - task_i * ntiles;
     const int64_t out_row = tasks[task_i].c;
-    const double* Bx = Xs + buf * C::XBUF + (wc * (C::TN * 8) + gq) * 16;
+    const double* Bx = Xs + buf * C::XBUF + (wc * (C::TN * 8) + pg) * 16;
 #pragma unroll 1
     for (int c = 0; c < C::NCH0; ++c) {
       const int nst = (st + 1 == C::NSTAGE) ? 0 : st + 1;
@@ -315,7 +325,7 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
       st = nst; ph = nph;
     }
     if (C::K1) {
-      const double* Bf = Fs + (wc * (C::TN * 8) + gq) * C::LDF + t;
+      const double* Bf = Fs + (wc * (C::TN * 8) + pg) * C::LDF + t;
 #pragma unroll 1
       for (int c = 0; c < C::NCH1; ++c) {
         const int nst = (st + 1 == C::NSTAGE) ? 0 : st + 1;
@@ -342,14 +352,15 @@ stream_leaf_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
     int64_t ldo;
     if (DOWN) { O = p.Y + out_row + (int64_t)tile * C::NT * p.ldy; ldo = p.ldy; }
     else { O = p.Z + out_row * (int64_t)nrhs + (int64_t)tile * C::NT * (R + 4); ldo = R + 4; }
-    O += (int64_t)(wc * (C::TN * 8) + 2 * t) * ldo + wr * (C::TM * 8) + gq;
-    const int colb = wc * (C::TN * 8) + 2 * t;
+    O += (int64_t)(wc * (C::TN * 8)) * ldo + wr * (C::TM * 8) + gq;
+    const int colb = wc * (C::TN * 8);
+    const int pc[2] = {perm8(2 * t), perm8(2 * t + 1)};  // columns of this lane's two accumulator elements
 #pragma unroll
     for (int j = 0; j < C::TN; ++j) {
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
-        const bool live = colb + j * 8 + e < ncols && !dbg_nostore;
-        double* dcol = O + (int64_t)(j * 8 + e) * ldo;
+        const bool live = colb + j * 8 + pc[e] < ncols && !dbg_nostore;
+        double* dcol = O + (int64_t)(j * 8 + pc[e]) * ldo;
 #pragma unroll
         for (int i = 0; i < C::TM; ++i) {
           if (live) {
@@ -626,8 +637,41 @@ static int make_x_map(CUtensorMap* map, const double* X, int64_t rows, int64_t n
   return HSSB_OK;
 }
 
+}  // namespace hssb
+#include "hssb_leaf2.cuh"
+namespace hssb {
+
+template <int M, int R, bool DOWN, int NT, int KC>
+static int launch_leaf2(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
+  using C = Leaf2Cfg<M, R, DOWN, NT, KC>;
+  FastState* fs = (FastState*)H->fast_state;
+  CUtensorMap xmap;
+  const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
+  const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
+  if (int rc = make_x_map(&xmap, cp.X, H->local_n, cp.nrhs, cp.ldx, C::NT)) return rc;
+  if (int rc = fs->configure((const void*)leaf2_kernel<M, R, DOWN, NT, KC>, C::SMEM)) return rc;
+  leaf2_kernel<M, R, DOWN, NT, KC><<<grid, C::NWARPS * 32 + 32, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp, xmap);
+  H->launches++;
+  HSSB_CUDA(cudaGetLastError());
+  return HSSB_OK;
+}
+
 template <int M, int R, bool DOWN, int NT>
 static int launch_leaf_nt(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
+  // second generation (self-contained ring stages, hssb_leaf2.cuh); HSSB_OPT_LEAF_KERNEL = 1 keeps the first
+  if (H->leaf_kernel != 1) {
+    if constexpr (DOWN) {
+      // longer chunks = fewer chunk boundaries (each costs ~100 cycles without DMMAs): 32 columns of [D U] per
+      // stage where the ring still holds 4 stages (measured: c3 0.687 -> 0.666 ms, c4 1.584 -> 1.534 ms)
+      if constexpr (M == 128 && R % 32 == 0) {
+        if (H->leaf_kernel != 3) return launch_leaf2<M, R, true, NT, 32>(H, ph, cp, st);
+      }
+      return launch_leaf2<M, R, true, NT, 16>(H, ph, cp, st);
+    } else {
+      if (H->leaf_kernel != 3) return launch_leaf2<M, R, false, NT, 64>(H, ph, cp, st);
+      return launch_leaf2<M, R, false, NT, 32>(H, ph, cp, st);
+    }
+  }
   using C = StreamCfg<M, R, DOWN, NT>;
   FastState* fs = (FastState*)H->fast_state;
   CUtensorMap xmap;

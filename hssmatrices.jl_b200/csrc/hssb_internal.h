@@ -234,6 +234,9 @@ struct hssb_matrix {
   void* fast_state = nullptr;
   // persistent tree kernel (hssb_tree.cuh): 1 = all merge / translate levels (and the peer exchange) in one
   // cooperative launch, 0 = one launch per level, 2 = as 1 without the cooperative attribute (diagnostics)
-  int tree_kernel = 1;
+  int tree_kernel = 0;
+  // leaf kernels: 2 = second generation (hssb_leaf2.cuh, default), 1 = first generation (hssb_fast.cuh, cross-check),
+  // 3 = second generation with longer chunks where instantiated (measurement)
+  int leaf_kernel = 2;
   void* tree_plan = nullptr;
 };

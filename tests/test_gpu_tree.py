@@ -35,7 +35,7 @@ def test_tree_kernel_matches_levels_and_oracle(gpu, oracle, n, ls, r):
     seed = 4242 + n + r
     h = oracle.synthetic_hss(n, ls, r, seed) if n <= 8192 else None
     with gpu.synthetic(n, ls, r, seed) as P:
-        assert P.get_option(gpu.OPT_TREE_KERNEL) == 1
+        assert P.get_option(gpu.OPT_TREE_KERNEL) == 0   # measured slower than graph-replayed level launches: opt-in
         for k in (1, 9, 20, 33, 64, 65, 130, 200):
             X = oracle.synth_x(seed + k, n, k)
             P.set_option(gpu.OPT_TREE_KERNEL, 1)

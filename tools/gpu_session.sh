@@ -5,8 +5,8 @@ tag=${1:-s}
 mkdir -p gpurun_out
 echo "== tree tests"; timeout 900 python -m pytest tests/test_gpu_tree.py -x -q > gpurun_out/${tag}_tree.log 2>&1; echo "rc=$?"; tail -3 gpurun_out/${tag}_tree.log
 echo "== trace"; timeout 300 python tools/tree_trace.py c3 c4 > gpurun_out/${tag}_trace.log 2>&1; echo "rc=$?"; grep total gpurun_out/${tag}_trace.log
-echo "== bench tree"; timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-extra --variant nosolve > gpurun_out/${tag}_bench_tree.json 2> gpurun_out/${tag}_bench_tree.err; echo "rc=$?"
-echo "== bench notree"; timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-extra --variant nosolve,notree > gpurun_out/${tag}_bench_notree.json 2> gpurun_out/${tag}_bench_notree.err; echo "rc=$?"
+echo "== bench default"; timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-extra --variant nosolve > gpurun_out/${tag}_bench_tree.json 2> gpurun_out/${tag}_bench_tree.err; echo "rc=$?"
+echo "== bench tree-kernel"; timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu --no-e2e --no-extra --variant nosolve,tree > gpurun_out/${tag}_bench_treek.json 2> gpurun_out/${tag}_bench_treek.err; echo "rc=$?"
 echo "== bench full default"; ( time timeout 900 python bench.py > gpurun_out/${tag}_bench_full.json 2> gpurun_out/${tag}_bench_full.err ) 2>&1 | grep real; echo "rc=$?"
 python - <<P
 import json,glob
