@@ -125,6 +125,16 @@ SIGNATURES = {
     "hssb_ulv_info": (C.c_int, [_P, _P]),
     "hssb_debug_ulv_factor_host": (C.c_int, [_P]),
     "hssb_debug_ulv_pool": (C.c_int, [_P, _P, _i64]),
+    "hssb_group_finalize": (C.c_int, [_P, _i64, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "hssb_group_create_synthetic": (C.c_int, [_i64, _i64, _i64, C.c_uint64, C.POINTER(C.c_int), C.c_int, C.POINTER(_P)]),
+    "hssb_group_destroy": (C.c_int, [_P]),
+    "hssb_group_size": (C.c_int, [_P]),
+    "hssb_group_shard": (_P, [_P, C.c_int]),
+    "hssb_group_reserve": (C.c_int, [_P, _i64]),
+    "hssb_group_matmul": (C.c_int, [_P, _i64, _i64, _i64, _P, _i64, _P, _i64, C.c_double, C.c_double]),
+    "hssb_group_matmul_t": (C.c_int, [_P, _i64, _i64, _i64, _P, _i64, _P, _i64, C.c_double, C.c_double]),
+    "hssb_group_matmul_dev": (C.c_int, [_P, _i64, C.POINTER(_P), _i64, C.POINTER(_P), _i64, C.c_double, C.c_double, C.POINTER(_P)]),
+    "hssb_group_sync": (C.c_int, [_P]),
 }
 
 OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS, OPT_ADJOINT_TWIN, OPT_ULV_FAST, OPT_TREE_KERNEL, OPT_HOST_BOUNCE, OPT_LAST_BOUNCE, OPT_LEAF_KERNEL = 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12
@@ -432,6 +442,125 @@ def synthetic(n, leafsize, rank, seed, device=0, shard_rank=0, n_shards=1, plan_
     return PackedHss(h)
 
 
+def _devs(devices):
+    devices = list(devices)
+    return (C.c_int * len(devices))(*devices), len(devices)
+
+
+def pack_group(hssA, devices):
+    """One process, several GPUs: shard `hssA` by subtree over `devices` (a power of two of them; entries may
+    repeat) behind ONE handle whose `@` / `mul_` take the whole X and Y (hssb_group_*)."""
+    L = lib()
+    b = C.c_void_p()
+    _check(L.hssb_builder_create(C.byref(b)))
+    try:
+        root = _build(b, hssA, 0, 1)       # the whole tree; every shard copies what it owns
+        g = C.c_void_p()
+        arr, nd = _devs(devices)
+        _check(L.hssb_group_finalize(b, root, arr, nd, C.byref(g)))
+    finally:
+        L.hssb_builder_destroy(b)
+    return PackedGroup(g)
+
+
+def synthetic_group(n, leafsize, rank, seed, devices):
+    """The synthetic benchmark matrix sharded over `devices` in one process."""
+    g = C.c_void_p()
+    arr, nd = _devs(devices)
+    _check(lib().hssb_group_create_synthetic(n, leafsize, rank, seed, arr, nd, C.byref(g)))
+    return PackedGroup(g)
+
+
+class PackedGroup:
+    """P sharded handles of one matrix in ONE process (hssb_group*): the Julia drop-in's multi-GPU form."""
+
+    __array_priority__ = 1000
+
+    def __init__(self, handle):
+        self._g = handle
+        L = lib()
+        self.size = L.hssb_group_size(self._g)
+        self.shards = []
+        for i in range(self.size):
+            sh = PackedHss.__new__(PackedHss)
+            sh._h = C.c_void_p(L.hssb_group_shard(self._g, i))
+            sh._borrowed = True
+            sh.info = _Info()
+            _check(L.hssb_info(sh._h, C.byref(sh.info)))
+            self.shards.append(sh)
+        self.m, self.n = self.shards[0].info.m, self.shards[0].info.n
+
+    def close(self):
+        if self._g:
+            for sh in self.shards:
+                sh._h = None
+            lib().hssb_group_destroy(self._g)
+            self._g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def reserve(self, max_nrhs):
+        _check(lib().hssb_group_reserve(self._g, max_nrhs))
+
+    def sync(self):
+        _check(lib().hssb_group_sync(self._g))
+
+    def set_option(self, opt, value):
+        for sh in self.shards:
+            sh.set_option(opt, value)
+
+    def launch_count(self):
+        return sum(sh.launch_count() for sh in self.shards)
+
+    def mul_(self, Cm, B, alpha=1.0, beta=0.0, trans=False):
+        """mul!(C, hssA, B, alpha, beta) on the whole host matrices; every shard works on its row block."""
+        B = np.asarray(B, dtype=np.float64)
+        if B.ndim != 2 or Cm.ndim != 2:
+            raise DimensionMismatch("B and C must be matrices")
+        if not (isinstance(Cm, np.ndarray) and Cm.dtype == np.float64 and Cm.flags.f_contiguous and Cm.flags.writeable):
+            raise TypeError("C must be a writable column-major float64 array (Julia Matrix{Float64})")
+        if Cm.shape[1] != B.shape[1]:
+            raise DimensionMismatch("Dimensions of C don't match up with A and B.")
+        Bf = _fcol(B)
+        fn = lib().hssb_group_matmul_t if trans else lib().hssb_group_matmul
+        _check(fn(self._g, Cm.shape[0], Bf.shape[0], Bf.shape[1], _ptr(Bf), max(Bf.shape[0], 1), _ptr(Cm), max(Cm.shape[0], 1),
+                  float(alpha), float(beta)))
+        return Cm
+
+    def __matmul__(self, B):
+        B = _f64(B)
+        if B.ndim == 1:
+            return (self @ B.reshape(-1, 1)).reshape(-1)
+        return self.mul_(np.empty((self.m, B.shape[1]), order="F"), B, 1.0, 0.0)
+
+    def tmatmul(self, B):
+        B = _f64(B)
+        if B.ndim == 1:
+            return self.tmatmul(B.reshape(-1, 1)).reshape(-1)
+        return self.mul_(np.empty((self.n, B.shape[1]), order="F"), B, 1.0, 0.0, trans=True)
+
+    def __rmatmul__(self, A):
+        A = _f64(A)
+        return self.tmatmul(np.asfortranarray(A.T)).T
+
+    def matmul_dev(self, dX, ldx, dY, ldy, nrhs, alpha=1.0, beta=0.0, streams=None):
+        """Device pointers (one per shard, on that shard's device) to the local row blocks; asynchronous."""
+        px = (C.c_void_p * self.size)(*dX)
+        py = (C.c_void_p * self.size)(*dY)
+        ps = (C.c_void_p * self.size)(*streams) if streams is not None else None
+        _check(lib().hssb_group_matmul_dev(self._g, nrhs, px, ldx, py, ldy, float(alpha), float(beta), ps))
+
+
 def load(path, device=0):
     """Load a packed matrix written by PackedHss.save(); device=-1 gives a host-only handle."""
     h = C.c_void_p()
@@ -452,7 +581,8 @@ class PackedHss:
     # lifetime --------------------------------------------------------------
     def close(self):
         if self._h:
-            lib().hssb_destroy(self._h)
+            if not getattr(self, "_borrowed", False):
+                lib().hssb_destroy(self._h)
             self._h = None
 
     def __del__(self):

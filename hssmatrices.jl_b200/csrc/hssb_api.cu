@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <functional>
 #include <memory>
+#include <mutex>
 #include <new>
 
 #include "hssb_internal.h"
@@ -27,11 +28,22 @@ namespace hssb {
 
 static thread_local char g_err[1024] = "";
 
+// Host-mapped words the kernels' bounded waits write to before they trap (hssb_fast.cuh: trap_report).
+static unsigned long long* g_trap_host = nullptr;
+
 void set_error(const char* fmt, ...) {
   va_list ap;
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+  if (g_trap_host && g_trap_host[0]) {  // a kernel gave up waiting: say for what
+    static const char* what[] = {"?", "a shared-memory mbarrier (TMA data or a ring slot)", "the grid barrier of the tree kernel",
+                                 "a peer's acknowledgement of the previous exchange", "a peer's subtree-root block (exchange)"};
+    const unsigned long long c = g_trap_host[0];
+    const size_t len = strlen(g_err);
+    snprintf(g_err + len, sizeof(g_err) - len, " [a kernel timed out waiting for %s: wanted %llu, saw %llu, block %llu thread %llu]",
+             what[c < 5 ? c : 0], g_trap_host[1], g_trap_host[2], g_trap_host[3] & 0xffffffffull, g_trap_host[3] >> 32);
+  }
 }
 
 static inline int64_t round_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -49,6 +61,24 @@ struct DeviceGuard {
   }
 };
 
+// One host-mapped block per process; every device's copy of g_trap_slot points at it.
+static int ensure_trap_slot(int device) {
+  static std::mutex mu;
+  static bool done[64] = {};
+  std::lock_guard<std::mutex> lk(mu);
+  if (device < 0 || device >= 64 || done[device]) return HSSB_OK;
+  DeviceGuard dg(device);
+  if (!g_trap_host) {
+    HSSB_CUDA(cudaHostAlloc((void**)&g_trap_host, 64, cudaHostAllocMapped | cudaHostAllocPortable));
+    memset(g_trap_host, 0, 64);
+  }
+  unsigned long long* dptr = nullptr;
+  HSSB_CUDA(cudaHostGetDevicePointer((void**)&dptr, g_trap_host, 0));
+  HSSB_CUDA(cudaMemcpyToSymbol(g_trap_slot, &dptr, sizeof(dptr)));
+  done[device] = true;
+  return HSSB_OK;
+}
+
 static int check_device(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -63,7 +93,7 @@ static int check_device(int device) {
   if (prop.major != 10)
     HSSB_FAIL(HSSB_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
               prop.minor);
-  return HSSB_OK;
+  return ensure_trap_slot(device);
 }
 
 // ----------------------------------------------------------------- builder ---
@@ -754,21 +784,32 @@ static void drop_twin(hssb_matrix* H) {
 }
 
 static void nodes_from_builder(const hssb_builder* b, int64_t root, hssb_matrix* H, std::vector<BlockSource>& src) {
-  std::vector<int64_t> order{root};
+  // BFS renumbering.  A builder that holds the WHOLE tree may be finalised once per shard: subtrees at the
+  // shard cut (depth log2 n_shards) that belong to other shards are turned into size-only placeholders
+  // here, exactly as if the caller had registered them with hssb_builder_add_remote.
+  int p = 0;
+  while ((1 << p) < H->n_shards) ++p;
+  struct Item { int64_t id; int depth; int64_t pos; bool pruned; };
+  std::vector<Item> order{{root, 0, 0, false}};
   for (size_t q = 0; q < order.size(); ++q) {
-    const BNode& bn = b->nodes[(size_t)order[q]];
-    if (!bn.leaf && !bn.remote) { order.push_back(bn.left); order.push_back(bn.right); }
+    const Item it = order[q];
+    const BNode& bn = b->nodes[(size_t)it.id];
+    if (H->n_shards > 1 && it.depth == p && it.pos != H->shard_rank && !bn.remote) { order[q].pruned = true; continue; }
+    if (!bn.leaf && !bn.remote) {
+      order.push_back({bn.left, it.depth + 1, 2 * it.pos, false});
+      order.push_back({bn.right, it.depth + 1, 2 * it.pos + 1, false});
+    }
   }
   std::vector<int64_t> newid(b->nodes.size(), -1);
-  for (size_t q = 0; q < order.size(); ++q) newid[(size_t)order[q]] = (int64_t)q;
+  for (size_t q = 0; q < order.size(); ++q) newid[(size_t)order[q].id] = (int64_t)q;
   H->nodes.resize(order.size());
   src.resize(order.size());
   for (size_t q = 0; q < order.size(); ++q) {
-    const BNode& bn = b->nodes[(size_t)order[q]];
+    const BNode& bn = b->nodes[(size_t)order[q].id];
     Node& t = H->nodes[q];
-    t.leaf = bn.leaf; t.remote = bn.remote;
+    t.leaf = bn.leaf && !order[q].pruned; t.remote = bn.remote || order[q].pruned;
     t.m = bn.m; t.n = bn.n; t.kr = bn.kr; t.kw = bn.kw;
-    if (!bn.leaf && !bn.remote) { t.left = newid[(size_t)bn.left]; t.right = newid[(size_t)bn.right]; }
+    if (!bn.leaf && !t.remote) { t.left = newid[(size_t)bn.left]; t.right = newid[(size_t)bn.right]; }
     for (int k = 0; k < BK_COUNT; ++k) src[q].blk[k] = &bn.blk[k];
   }
 }
@@ -888,10 +929,10 @@ __device__ __forceinline__ unsigned long long ld_volatile_sys(const unsigned lon
   asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void spin_until_ge(const unsigned long long* p, unsigned long long want) {
+__device__ __forceinline__ void spin_until_ge(const unsigned long long* p, unsigned long long want, unsigned long long what) {
   const long long t0 = clock64();
   while (ld_volatile_sys(p) < want) {
-    if (clock64() - t0 > 8000000000ll) __trap();  // a lost peer must surface as an error, not a hang
+    if (clock64() - t0 > 8000000000ll) trap_report(what, want, ld_volatile_sys(p));  // a lost peer must surface as an error, not a hang
   }
 }
 
@@ -903,7 +944,7 @@ __global__ void __launch_bounds__(256) xchg_push_kernel(XchgParams q) {
   __syncthreads();
   const unsigned long long e = s_epoch;
   // peers must have consumed the previous epoch before their copy of my slot is overwritten
-  if ((int)threadIdx.x < P && (int)threadIdx.x != me) spin_until_ge(mine + P + threadIdx.x, e - 1);
+  if ((int)threadIdx.x < P && (int)threadIdx.x != me) spin_until_ge(mine + P + threadIdx.x, e - 1, TRAP_PEER_ACK);
   __syncthreads();
   const double2* src = reinterpret_cast<const double2*>(q.z[me] + q.slot_off + (long long)me * q.slot_elems);
   const long long n2 = q.slot_elems / 2;
@@ -922,7 +963,7 @@ __global__ void __launch_bounds__(256) xchg_push_kernel(XchgParams q) {
     if ((int)threadIdx.x < P && (int)threadIdx.x != me) {
       __threadfence_system();
       asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(q.flags[threadIdx.x] + me), "l"(e) : "memory");
-      spin_until_ge(mine + threadIdx.x, e);
+      spin_until_ge(mine + threadIdx.x, e, TRAP_PEER_DATA);
     }
     __syncthreads();
     __threadfence_system();
@@ -1068,6 +1109,7 @@ static bool same_call(const CallParams& a, const CallParams& b) {
 static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
   for (auto& g : H->graphs)
     if (same_call(g.cp, cp)) {
+      if (H->prepare_only) return HSSB_OK;
       HSSB_CUDA(cudaGraphLaunch(g.exec, st));
       H->launches += g.kernels;
       return HSSB_OK;
@@ -1091,6 +1133,10 @@ static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) { cudaGetLastError(); HSSB_FAIL(HSSB_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
   H->graphs.push_back(slot);
+  if (H->prepare_only) {  // upload now, so that the first replay has nothing left to set up
+    HSSB_CUDA(cudaGraphUpload(slot.exec, st));
+    return HSSB_OK;
+  }
   HSSB_CUDA(cudaGraphLaunch(slot.exec, st));
   H->launches += kernels;
   return HSSB_OK;
@@ -1242,7 +1288,7 @@ int hssb_destroy(hssb_matrix* h) {
   for (auto e : h->prof_events) cudaEventDestroy(e);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   for (int r = 0; r < hssb_matrix::MAX_PEERS; ++r)
-    if (h->peer_xchg && r != h->shard_rank && r < h->n_shards) {
+    if (h->peer_xchg && !h->peer_inprocess && r != h->shard_rank && r < h->n_shards) {
       if (h->peer_z[r]) cudaIpcCloseMemHandle(h->peer_z[r]);
       if (h->peer_flags[r]) cudaIpcCloseMemHandle(h->peer_flags[r]);
     }
@@ -1386,11 +1432,49 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
   // graph replay: always for the host entry (its staging pointers are stable), on request for
   // caller-owned device pointers (a new pointer set costs a capture + instantiate)
   if ((h->use_graph || h->in_host_call) && !h->profile) return run_graph(h, cp, st);
+  if (h->prepare_only) return HSSB_OK;  // plain launches have nothing to capture ahead of time
   return run_phases(h, cp, st);
 }
 
+// Device staging buffers, copy streams and events of the host-pointer entry (allocates, and cudaFree
+// synchronises the device: callers that run several shards of one device concurrently do this up front).
+static int ensure_host_entry(hssb_matrix* h, int64_t nrhs) {
+  if (nrhs > h->stage_nrhs) {
+    cudaFree(h->x_stage); cudaFree(h->y_stage);
+    h->x_stage = h->y_stage = nullptr; h->stage_nrhs = 0;
+    const size_t rmax = (size_t)std::max<int64_t>(std::max(h->local_n, h->local_m), 1);  // either stage may hold X or Y (A or A')
+    const size_t xb = rmax * (size_t)nrhs * 8, yb = rmax * (size_t)nrhs * 8;
+    if (cudaMalloc(&h->x_stage, xb) != cudaSuccess || cudaMalloc(&h->y_stage, yb) != cudaSuccess) {
+      cudaGetLastError();
+      HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of X/Y staging (%.3f GB) failed", (xb + yb) * 1e-9);
+    }
+    h->stage_nrhs = nrhs;
+    invalidate_graphs(h);
+  }
+  if (!h->copy_in) {
+    HSSB_CUDA(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+    HSSB_CUDA(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+    for (int i = 0; i < hssb_matrix::MAX_BLOCKS; ++i) {
+      HSSB_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
+      HSSB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
+    }
+  }
+  return HSSB_OK;
+}
+
+static int ensure_bounce(hssb_matrix* h) {
+  if (h->bounce) return HSSB_OK;
+  Bounce* bn = new (std::nothrow) Bounce();
+  if (!bn) HSSB_FAIL(HSSB_ERR_ALLOC, "hssb_matmul: out of memory");
+  if (int rc = bn->init(h->device)) { delete bn; return rc; }
+  h->bounce = bn;
+  return HSSB_OK;
+}
+
+// prepare = true: everything the call needs is allocated, captured and instantiated, nothing is copied or launched
+// (hssb_group: the shards of one call are prepared one after the other and only then run concurrently).
 static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx,
-                            double* Y, int64_t ldy, double alpha, double beta) {
+                            double* Y, int64_t ldy, double alpha, double beta, bool prepare = false) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
   if (trans == 2 && h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
   const int64_t need_x = trans ? h->local_m : h->local_n, need_y = trans ? h->local_n : h->local_m;
@@ -1414,32 +1498,8 @@ static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t r
     const int a = prepare_solve(h);
     if (a) return a;
   }
-  if (nrhs > h->stage_nrhs) {
-    cudaFree(h->x_stage); cudaFree(h->y_stage);
-    h->x_stage = h->y_stage = nullptr; h->stage_nrhs = 0;
-    const size_t rmax = (size_t)std::max<int64_t>(std::max(h->local_n, h->local_m), 1);  // either stage may hold X or Y (A or A')
-    const size_t xb = rmax * (size_t)nrhs * 8, yb = rmax * (size_t)nrhs * 8;
-    if (cudaMalloc(&h->x_stage, xb) != cudaSuccess || cudaMalloc(&h->y_stage, yb) != cudaSuccess) {
-      cudaGetLastError();
-      HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of X/Y staging (%.3f GB) failed", (xb + yb) * 1e-9);
-    }
-    h->stage_nrhs = nrhs;
-    invalidate_graphs(h);
-  }
+  if (int rc = ensure_host_entry(h, nrhs)) return rc;
   const int64_t sx = std::max<int64_t>(rows_x, 1), sy = rows_y;
-  // The product is independent per right-hand side, so the call is pipelined over column blocks:
-  // H2D of block j+1 (copy-in stream), the product of block j (compute stream) and D2H of block
-  // j-1 (copy-out stream) overlap; PCIe is full duplex.  The transfers dominate (2*n*nrhs*8 bytes
-  // over PCIe against ~1 ms of kernels), so the blocks are small (about nrhs/8 columns) even
-  // though narrow blocks leave the kernels' column tiles partly empty.
-  if (!h->copy_in) {
-    HSSB_CUDA(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
-    HSSB_CUDA(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
-    for (int i = 0; i < hssb_matrix::MAX_BLOCKS; ++i) {
-      HSSB_CUDA(cudaEventCreateWithFlags(&h->ev_in[i], cudaEventDisableTiming));
-      HSSB_CUDA(cudaEventCreateWithFlags(&h->ev_done[i], cudaEventDisableTiming));
-    }
-  }
   // every shard must cut the call into the same blocks (each block contains the exchange step)
   const int64_t rows_eff = h->n_shards > 1 ? (h->m + h->n) / h->n_shards : rows_x + rows_y;
   int64_t cb = nrhs;
@@ -1453,12 +1513,21 @@ static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t r
   const bool big = (rows_x + rows_y) * nrhs * 8 >= ((int64_t)16 << 20);
   const bool bounce_in = rows_x > 0 && h->host_bounce && (h->host_bounce == 2 || (big && host_ptr_pageable(X)));
   const bool bounce_out = h->host_bounce && (h->host_bounce == 2 || (big && host_ptr_pageable(Y)));
+  if (bounce_in || bounce_out) {
+    if (int rc = ensure_bounce(h)) return rc;
+  }
   Bounce* bn = (Bounce*)h->bounce;
-  if ((bounce_in || bounce_out) && !bn) {
-    bn = new (std::nothrow) Bounce();
-    if (!bn) HSSB_FAIL(HSSB_ERR_ALLOC, "hssb_matmul: out of memory");
-    if (int rc = bn->init(h->device)) { delete bn; return rc; }
-    h->bounce = bn;
+  if (prepare) {
+    if (h->profile) return HSSB_OK;  // profiled calls launch phase by phase: nothing to capture
+    int rc = HSSB_OK;
+    h->in_host_call = h->prepare_only = true;
+    for (int64_t j = 0; j < nblk && !rc; ++j) {
+      const int64_t c0 = j * cb, nc = std::min(cb, nrhs - c0);
+      rc = matmul_dev_impl(h, trans, rows_y, rows_x, nc, h->x_stage + c0 * sx, sx, h->y_stage + c0 * sy, sy, alpha, beta, h->stream);
+    }
+    h->in_host_call = h->prepare_only = false;
+    if (!rc) HSSB_CUDA(cudaStreamSynchronize(h->stream));
+    return rc;
   }
   h->last_bounce = (bounce_in ? 1 : 0) | (bounce_out ? 2 : 0);
   std::vector<Latch> in_latch((size_t)(bounce_in ? nblk : 0));
@@ -2019,3 +2088,5 @@ int hssb_debug_ulv_pool(const hssb_matrix* h, double* out, int64_t len) {
 }
 
 }  // extern "C"
+
+#include "hssb_group.h"

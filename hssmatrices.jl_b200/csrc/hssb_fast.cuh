@@ -50,12 +50,26 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (and surface as a CUDA error), never hang the GPU.
+// Bounded waits: a protocol bug must trap (and surface as a CUDA error), never hang the GPU.  Before the trap the
+// waiter says what it was waiting for in host-mapped memory (the context is gone afterwards, host memory is not);
+// set_error() appends it to the CUDA error text.
+enum TrapCode : unsigned long long { TRAP_MBAR = 1, TRAP_GRID = 2, TRAP_PEER_ACK = 3, TRAP_PEER_DATA = 4 };
+static __device__ unsigned long long* g_trap_slot = nullptr;
+__device__ __noinline__ void trap_report(unsigned long long code, unsigned long long a, unsigned long long b) {
+  unsigned long long* s = g_trap_slot;
+  if (s) {
+    s[1] = a; s[2] = b; s[3] = (unsigned long long)blockIdx.x | ((unsigned long long)threadIdx.x << 32);
+    __threadfence_system();
+    s[0] = code;
+    __threadfence_system();
+  }
+  __trap();
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
   const long long t0 = clock64();
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000ll) __trap();
+    if (clock64() - t0 > 4000000000ll) trap_report(TRAP_MBAR, smem_u32(bar), parity);
   }
 }
 // 1-D bulk copy global -> shared (UBLKCP), completion counted in bytes on an mbarrier.

@@ -209,6 +209,7 @@ struct hssb_matrix {
   static constexpr int MAX_PEERS = 16;
   bool peer_xchg = false;
   bool xchg_exported = false;
+  bool peer_inprocess = false;  // peer tables point at other handles of this process (hssb_group), not at IPC mappings
   double* peer_z[MAX_PEERS] = {};
   unsigned long long* peer_flags[MAX_PEERS] = {};  // [0,P): data flags, [P,2P): ack flags, [2P]: epoch, [2P+1]: ticket
   unsigned long long* my_flags = nullptr;
@@ -216,6 +217,7 @@ struct hssb_matrix {
   bool force_generic = false, use_graph = false, profile = false;
   int debug_mode = 0;
   bool in_host_call = false;
+  bool prepare_only = false;  // run_graph captures, instantiates and uploads but does not launch
   std::vector<cudaEvent_t> prof_events;  // HSSB_OPT_PROFILE: one event between consecutive phases
   int64_t prof_nrhs = 0;
   int prof_mode = 0;  // which plan the last profiled call ran (0 product, 1 transposed task table, 2 ULV solve)

@@ -88,7 +88,7 @@ __device__ __forceinline__ void grid_wait(const unsigned long long* arrive, int 
       }
       done = v[0] >= target && v[1] >= target && v[2] >= target && v[3] >= target;
       done = __all_sync(0xffffffffu, done);
-      if (!done && clock64() - t0 > 8000000000ll) __trap();  // a lost CTA must surface as an error, not a hang
+      if (!done && clock64() - t0 > 8000000000ll) trap_report(TRAP_GRID, target, (unsigned long long)base);  // a lost CTA must surface as an error, not a hang
     } while (!done);
   }
   asm volatile("fence.acq_rel.gpu;" ::: "memory");  // one acquire for all the relaxed polls
@@ -388,7 +388,7 @@ tree_kernel(const GTask* __restrict__ tasks, const TreeStep* __restrict__ steps,
           if (pusher || cta == 0) grid_wait(arrive, ncta, base + j, lane);  // the subtree-root Z block is complete
           if (pusher) {
             // the peer must have consumed the previous epoch before its copy of my slot is overwritten
-            if (lane == 0) spin_until_ge(mine + P + peer, e - 1);
+            if (lane == 0) spin_until_ge(mine + P + peer, e - 1, TRAP_PEER_ACK);
             __syncwarp();
             const long long n2 = xq.slot_elems / 2;
             const long long i0 = n2 * part / XCHG_PARTS, i1 = n2 * (part + 1) / XCHG_PARTS;
@@ -402,7 +402,7 @@ tree_kernel(const GTask* __restrict__ tasks, const TreeStep* __restrict__ steps,
           }
           if (cta == 0) {  // everybody else's slot has landed in my workspace
             for (int w = lane; w < P * XCHG_PARTS; w += 32)
-              if (w / XCHG_PARTS != me) spin_until_ge(mine + XCHG_PART0 + w, e);
+              if (w / XCHG_PARTS != me) spin_until_ge(mine + XCHG_PART0 + w, e, TRAP_PEER_DATA);
             __threadfence_system();
             __syncwarp();
           }

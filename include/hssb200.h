@@ -258,6 +258,37 @@ int hssb_comm_init(hssb_matrix* h, const void* id128, int rank, int n_ranks);
 int hssb_xchg_export(hssb_matrix* h, void* handle128);
 int hssb_xchg_import(hssb_matrix* h, const void* all_handles, int n_ranks);
 
+/* ---- one process, one call, P devices ("a single ccall from one Julia thread drives all GPUs") ----
+ * A group holds P sharded handles of one matrix, shard g (the g-th subtree at depth log2 P plus the
+ * replicated top tree) on devices[g], wired to each other in process: the devices enable peer access
+ * and the exchange kernels store into the peers' workspaces directly (no IPC, no NCCL, no MPI.jl).  This
+ * is what the Julia drop-in `hssA * X` (matmul.jl:13) uses when more than one GPU is asked for.  P is a
+ * power of two <= 16 and the tree must be at least log2 P deep.  Entries of `devices` may repeat, at most twice each (two
+ * shards on one GPU: slower, but exercises the sharded path on a single-GPU box).
+ *   hssb_group_finalize          from a builder that holds the WHOLE tree (every shard copies what it owns)
+ *   hssb_group_create_synthetic  the benchmark matrices, generated per shard on its device
+ *   hssb_group_matmul[_t]        X, Y = the whole host matrices (same contract as hssb_matmul[_t]); every shard
+ *                                runs the pipelined host entry on its row block, all of them concurrently
+ *   hssb_group_matmul_dev        dX[g] / dY[g] = device pointers ON devices[g] to shard g's row blocks (leading
+ *                                dimensions ldx / ldy), asynchronous on streams[g] (NULL table: each shard's own
+ *                                stream, wait with hssb_group_sync)
+ *   hssb_group_shard             borrow shard g's handle (options, hssb_info, ...); owned by the group          */
+typedef struct hssb_group hssb_group;
+int hssb_group_finalize(hssb_builder* b, int64_t root, const int* devices, int n_devices, hssb_group** out);
+int hssb_group_create_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, const int* devices, int n_devices,
+                                hssb_group** out);
+int hssb_group_destroy(hssb_group* g);
+int hssb_group_size(const hssb_group* g);
+hssb_matrix* hssb_group_shard(hssb_group* g, int i);
+int hssb_group_reserve(hssb_group* g, int64_t max_nrhs);
+int hssb_group_matmul(hssb_group* g, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx, double* Y, int64_t ldy,
+                      double alpha, double beta);
+int hssb_group_matmul_t(hssb_group* g, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx, double* Y,
+                        int64_t ldy, double alpha, double beta);
+int hssb_group_matmul_dev(hssb_group* g, int64_t nrhs, const double* const* dX, int64_t ldx, double* const* dY, int64_t ldy, double alpha,
+                          double beta, void* const* streams);
+int hssb_group_sync(hssb_group* g);
+
 /* ---- measurement helpers (used by bench.py; not on the product path) --- */
 /* kind 0: FP64 FMA (DFMA) register-resident peak, kind 1: FP64 tensor (DMMA
  * m8n8k4) peak, returns TFLOP/s.  kind 2: device copy bandwidth over `bytes`

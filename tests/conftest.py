@@ -3,6 +3,12 @@ import sys
 
 import pytest
 
+# tests/test_gpu_group.py puts two shards of one matrix on ONE GPU (their kernels wait for each other): they need
+# their own hardware work queues, and no kernel may be loaded lazily (a load can synchronise the device) while
+# the other shard is already waiting.  Must be in the environment before the first CUDA call of the process.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests"), os.path.join(ROOT, "tests", "golden")):
     if p not in sys.path:

@@ -228,6 +228,43 @@ def test_sharded_from_host_tree(hb, oracle):
     assert relerr(np.vstack(Ys), ref) <= TOL
 
 
+def test_sharding_a_whole_builder_tree(hb, oracle):
+    """hssb_group_finalize registers the WHOLE tree once and finalises it once per shard: the packer then turns
+    the other shards' subtrees into placeholders itself.  Same plan, same pool as with hand-made
+    hssb_builder_add_remote placeholders."""
+    import ctypes as C
+    rng = np.random.default_rng(22)
+    n, k, P_ = 900, 4, 4
+    cl = oracle.bisection_cluster(n, 60)
+    h = oracle.random_hss(cl, cl, rng, 1, 8)
+    X = rng.standard_normal((n, k))
+    tree = to_product_tree(hb, h)
+    L = hb.lib()
+    b = C.c_void_p()
+    hb._check(L.hssb_builder_create(C.byref(b)))
+    try:
+        root = hb._build(b, tree, 0, 1)     # no placeholders registered
+        packs = []
+        for g in range(P_):
+            hd = C.c_void_p()
+            hb._check(L.hssb_plan_only(b, root, g, P_, C.byref(hd)))
+            packs.append(hb.PackedHss(hd))
+    finally:
+        L.hssb_builder_destroy(b)
+    manual = [hb.pack(tree, shard_rank=g, n_shards=P_, plan_only=True) for g in range(P_)]
+    for a, m in zip(packs, manual):
+        (ta, pa, poola), (tm, pm, poolm) = a.debug_plan(), m.debug_plan()
+        assert len(ta) == len(tm) and len(pa) == len(pm) and np.array_equal(poola, poolm)
+        assert all(bytes(x) == bytes(y) for x, y in zip(ta, tm))
+    Xs, Ys = [], []
+    for p in packs:
+        r0, m = p.info.local_col0, p.info.local_n
+        Xs.append(X[r0:r0 + m])
+        Ys.append(np.full((p.info.local_m, k), np.nan, order="F"))
+    plan_interp.run_sharded(packs, Xs, Ys)
+    assert relerr(np.vstack(Ys), oracle.matmul(h, X)) <= TOL
+
+
 def test_save_load_roundtrip(hb, oracle, tmp_path):
     """Packed format as a file: same blocks, same plan after a round trip."""
     rng = np.random.default_rng(31)
