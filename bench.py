@@ -294,7 +294,7 @@ class Run:
             flag = torch.tensor([ok], device="cuda")
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if flag.item() == 1:
-                self.exchange = "nvlink peer stores (CUDA IPC)" + (", inside the tree kernel" if "notree" not in variants else "")
+                self.exchange = "nvlink peer stores (CUDA IPC)" + (", inside the tree kernel" if "tree" in variants else ", one push kernel per product")
             else:                              # no peer access on this box: rebuild and use NCCL
                 P.close()
                 P = make()

@@ -1147,12 +1147,27 @@ static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
 using namespace hssb;
 
 // =============================================================== C ABI =====
+// No exception may cross the C ABI (std::vector growth, std::string, std::thread can throw).
+template <class R, class F>
+static R guarded(F&& f) {
+  try {
+    return f();
+  } catch (const std::bad_alloc&) {
+    set_error("out of host memory");
+    return (R)HSSB_ERR_ALLOC;
+  } catch (const std::exception& e) {
+    set_error("internal error: %s", e.what());
+    return (R)HSSB_ERR_STATE;
+  }
+}
+
 extern "C" {
 
 int hssb_version(void) { return HSSB_VERSION; }
 const char* hssb_last_error(void) { return g_err; }
 
 int hssb_device_count(void) {
+  return guarded<int>([&]() -> int {
   int n = 0;
   if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
   int ok = 0;
@@ -1161,19 +1176,23 @@ int hssb_device_count(void) {
     if (cudaGetDeviceProperties(&p, i) == cudaSuccess && p.major == 10) ++ok;
   }
   return ok;
+  });
 }
 
 int hssb_builder_create(hssb_builder** out) {
+  return guarded<int>([&]() -> int {
   if (!out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_builder_create: out is NULL");
   *out = new (std::nothrow) hssb_builder();
   if (!*out) HSSB_FAIL(HSSB_ERR_ALLOC, "hssb_builder_create: out of memory");
   return HSSB_OK;
+  });
 }
 
 void hssb_builder_destroy(hssb_builder* b) { delete b; }
 
 int64_t hssb_builder_add_leaf(hssb_builder* b, int64_t m, int64_t n, int64_t kr, int64_t kw, const double* D, int64_t ldd,
                               const double* U, int64_t ldu, const double* V, int64_t ldv) {
+  return guarded<int64_t>([&]() -> int64_t {
   if (!b) HSSB_FAIL(HSSB_ERR_ARG, "add_leaf: builder is NULL");
   if (m < 0 || n < 0 || kr < 0 || kw < 0) HSSB_FAIL(HSSB_ERR_ARG, "add_leaf: negative size");
   if (m > INT32_MAX || n > INT32_MAX || kr > INT32_MAX || kw > INT32_MAX) HSSB_FAIL(HSSB_ERR_ARG, "add_leaf: block too large");
@@ -1185,21 +1204,25 @@ int64_t hssb_builder_add_leaf(hssb_builder* b, int64_t m, int64_t n, int64_t kr,
   if ((rc = copy_block(nd.blk[BK_V], V, ldv, n, kw, "add_leaf V"))) return rc;  // rows(V) == cols(D): hssmatrix.jl:42
   b->nodes.push_back(std::move(nd));
   return (int64_t)b->nodes.size() - 1;
+  });
 }
 
 int64_t hssb_builder_add_remote(hssb_builder* b, int64_t m, int64_t n, int64_t kr, int64_t kw) {
+  return guarded<int64_t>([&]() -> int64_t {
   if (!b) HSSB_FAIL(HSSB_ERR_ARG, "add_remote: builder is NULL");
   if (m < 0 || n < 0 || kr < 0 || kw < 0) HSSB_FAIL(HSSB_ERR_ARG, "add_remote: negative size");
   BNode nd;
   nd.remote = true; nd.m = m; nd.n = n; nd.kr = kr; nd.kw = kw;
   b->nodes.push_back(std::move(nd));
   return (int64_t)b->nodes.size() - 1;
+  });
 }
 
 int64_t hssb_builder_add_branch(hssb_builder* b, int64_t left, int64_t right, int64_t kr, int64_t kw, const double* B12,
                                 int64_t ldb12, const double* B21, int64_t ldb21, const double* R1, int64_t ldr1,
                                 const double* W1, int64_t ldw1, const double* R2, int64_t ldr2, const double* W2,
                                 int64_t ldw2) {
+  return guarded<int64_t>([&]() -> int64_t {
   if (!b) HSSB_FAIL(HSSB_ERR_ARG, "add_branch: builder is NULL");
   const int64_t nn = (int64_t)b->nodes.size();
   if (left < 0 || left >= nn || right < 0 || right >= nn || left == right)
@@ -1223,9 +1246,11 @@ int64_t hssb_builder_add_branch(hssb_builder* b, int64_t left, int64_t right, in
   l.used = r.used = true;
   b->nodes.push_back(std::move(nd));
   return (int64_t)b->nodes.size() - 1;
+  });
 }
 
 int hssb_builder_finalize(hssb_builder* b, int64_t root, int device, int shard_rank, int n_shards, hssb_matrix** out) {
+  return guarded<int>([&]() -> int {
   if (!b || !out) HSSB_FAIL(HSSB_ERR_ARG, "finalize: NULL argument");
   *out = nullptr;
   if (root < 0 || root >= (int64_t)b->nodes.size()) HSSB_FAIL(HSSB_ERR_ARG, "finalize: invalid root id");
@@ -1240,10 +1265,12 @@ int hssb_builder_finalize(hssb_builder* b, int64_t root, int device, int shard_r
   if (rc) { hssb_destroy(H.release()); return rc; }
   *out = H.release();
   return HSSB_OK;
+  });
 }
 
 int hssb_create_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, int device, int shard_rank,
                           int n_shards, hssb_matrix** out) {
+  return guarded<int>([&]() -> int {
   if (!out) HSSB_FAIL(HSSB_ERR_ARG, "create_synthetic: out is NULL");
   *out = nullptr;
   if (n <= 0 || leafsize <= 0 || rank < 0 || rank > INT32_MAX) HSSB_FAIL(HSSB_ERR_ARG, "create_synthetic: bad sizes");
@@ -1260,10 +1287,12 @@ int hssb_create_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t se
   if (rc) { hssb_destroy(H.release()); return rc; }
   *out = H.release();
   return HSSB_OK;
+  });
 }
 
 int hssb_synthetic_rhs(uint64_t seed, int64_t n, int64_t nrhs, int64_t row0, int64_t rows, double* dX, int64_t ldx,
                        int device, void* stream) {
+  return guarded<int>([&]() -> int {
   if (!dX || n <= 0 || nrhs < 0 || rows < 0 || row0 < 0 || row0 + rows > n || ldx < rows)
     HSSB_FAIL(HSSB_ERR_ARG, "synthetic_rhs: bad arguments");
   int rc = check_device(device);
@@ -1275,9 +1304,11 @@ int hssb_synthetic_rhs(uint64_t seed, int64_t n, int64_t nrhs, int64_t row0, int
   synth_rhs_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(synth_key(seed, 0, KIND_X), n, nrhs, row0, rows, dX, ldx);
   HSSB_CUDA(cudaGetLastError());
   return HSSB_OK;
+  });
 }
 
 int hssb_destroy(hssb_matrix* h) {
+  return guarded<int>([&]() -> int {
   if (!h) return HSSB_OK;
   if (h->device < 0) { delete h; return HSSB_OK; }
   DeviceGuard dg(h->device);
@@ -1311,9 +1342,11 @@ int hssb_destroy(hssb_matrix* h) {
   cudaGetLastError();
   delete h;
   return HSSB_OK;
+  });
 }
 
 int hssb_info(const hssb_matrix* h, hssb_info_t* o) {
+  return guarded<int>([&]() -> int {
   if (!h || !o) HSSB_FAIL(HSSB_ERR_ARG, "hssb_info: NULL argument");
   memset(o, 0, sizeof(*o));
   o->m = h->m; o->n = h->n; o->local_m = h->local_m; o->local_n = h->local_n;
@@ -1325,9 +1358,11 @@ int hssb_info(const hssb_matrix* h, hssb_info_t* o) {
   o->shard_rank = h->shard_rank; o->n_shards = h->n_shards; o->device = h->device;
   o->uniform = h->uniform ? 1 : 0;
   return HSSB_OK;
+  });
 }
 
 int hssb_node_info(const hssb_matrix* h, int64_t node, hssb_node_t* o) {
+  return guarded<int>([&]() -> int {
   if (!h || !o) HSSB_FAIL(HSSB_ERR_ARG, "hssb_node_info: NULL argument");
   if (node < 0 || node >= (int64_t)h->nodes.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_node_info: node id out of range");
   const Node& t = h->nodes[(size_t)node];
@@ -1335,9 +1370,11 @@ int hssb_node_info(const hssb_matrix* h, int64_t node, hssb_node_t* o) {
   o->depth = t.depth; o->is_leaf = t.leaf; o->is_remote = t.remote;
   o->row0 = t.row0; o->m = t.m; o->col0 = t.col0; o->n = t.n; o->kr = t.kr; o->kw = t.kw;
   return HSSB_OK;
+  });
 }
 
 int hssb_get_block(const hssb_matrix* h, int64_t node, int kind, double* out, int64_t out_len) {
+  return guarded<int>([&]() -> int {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_get_block: NULL handle");
   if (node < 0 || node >= (int64_t)h->nodes.size() || kind < 0 || kind >= BK_COUNT)
     HSSB_FAIL(HSSB_ERR_ARG, "hssb_get_block: bad node or kind");
@@ -1362,13 +1399,16 @@ int hssb_get_block(const hssb_matrix* h, int64_t node, int kind, double* out, in
     memcpy(out, tmp.data(), tmp.size() * 8);
   }
   return HSSB_OK;
+  });
 }
 
 int hssb_reserve(hssb_matrix* h, int64_t max_nrhs) {
+  return guarded<int>([&]() -> int {
   if (!h || max_nrhs < 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_reserve: bad argument");
   if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle has no device");
   DeviceGuard dg(h->device);
   return ensure_workspace(h, max_nrhs);
+  });
 }
 
 // How Y = A' X runs: 0 = forward plan over the adjoint twin pool, 1 = any-shape transposed task
@@ -1620,6 +1660,7 @@ int hssb_matmul_t_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nr
 
 // hssA \ B (hssmatrix.jl:234 -> ulvfactsolve, ulvfactor.jl:10-19)
 int hssb_ulv_factor(hssb_matrix* h) {
+  return guarded<int>([&]() -> int {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_ulv_factor: NULL handle");
   if (h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_ulv_factor: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
   if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle: hssb200 has no CPU fallback, the factorisation needs a B200");
@@ -1627,6 +1668,7 @@ int hssb_ulv_factor(hssb_matrix* h) {
   if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
   invalidate_graphs(h);
   return ulv_factor_device(h);
+  });
 }
 
 int hssb_solve(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* B, int64_t ldb, double* Z, int64_t ldz) {
@@ -1639,6 +1681,7 @@ int hssb_solve_dev(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* dB,
 }
 
 int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* o) {
+  return guarded<int>([&]() -> int {
   if (!h || !o) HSSB_FAIL(HSSB_ERR_ARG, "hssb_ulv_info: NULL argument");
   memset(o, 0, sizeof(*o));
   o->supported = h->ulv.empty() ? 0 : 1;
@@ -1649,14 +1692,17 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* o) {
     o->z_rows = h->ulv_z_rows; o->f_rows = h->ulv_f_rows;
   }
   return HSSB_OK;
+  });
 }
 
 int hssb_sync(hssb_matrix* h) {
+  return guarded<int>([&]() -> int {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_sync: NULL handle");
   if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle has no device");
   DeviceGuard dg(h->device);
   HSSB_CUDA(cudaStreamSynchronize(h->stream));
   return HSSB_OK;
+  });
 }
 
 // HSSB_OPT_ULV_FAST: the ULV plan (tasks after ulv_task0, factor-pool layout, workspace rows) is rebuilt in
@@ -1685,6 +1731,7 @@ static int rebuild_ulv_plan(hssb_matrix* h) {
 }
 
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
+  return guarded<int>([&]() -> int {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_set_option: NULL handle");
   switch (opt) {
     case HSSB_OPT_FORCE_GENERIC: h->force_generic = value != 0; break;
@@ -1719,9 +1766,11 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
     drop_twin(h);
   }
   return HSSB_OK;
+  });
 }
 
 int64_t hssb_get_option(const hssb_matrix* h, int opt) {
+  return guarded<int64_t>([&]() -> int64_t {
   if (!h) return -1;
   switch (opt) {
     case HSSB_OPT_FORCE_GENERIC: return h->force_generic;
@@ -1737,6 +1786,7 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
     case HSSB_OPT_LAST_BOUNCE: return h->last_bounce;
     default: return -1;
   }
+  });
 }
 
 int64_t hssb_launch_count(const hssb_matrix* h) { return h ? h->launches : 0; }
@@ -1744,6 +1794,7 @@ int64_t hssb_launch_count(const hssb_matrix* h) { return h ? h->launches : 0; }
 int hssb_phase_count(const hssb_matrix* h) { return h ? (int)phase_list(h, h->prof_mode).size() : 0; }
 
 int hssb_phase_time(hssb_matrix* h, int i, hssb_phase_time_t* o) {
+  return guarded<int64_t>([&]() -> int64_t {
   if (!h || !o || i < 0 || i >= (int)phase_list(h, h->prof_mode).size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_phase_time: bad argument");
   const Phase& ph = phase_list(h, h->prof_mode)[(size_t)i];
   memset(o, 0, sizeof(*o));
@@ -1766,17 +1817,21 @@ int hssb_phase_time(hssb_matrix* h, int i, hssb_phase_time_t* o) {
     o->ms = ms;
   }
   return HSSB_OK;
+  });
 }
 
 int hssb_comm_unique_id(void* id128) {
+  return guarded<int>([&]() -> int {
   if (!id128) HSSB_FAIL(HSSB_ERR_ARG, "hssb_comm_unique_id: NULL buffer");
   int rc = load_nccl();
   if (rc) return rc;
   HSSB_NCCL(g_nccl.GetUniqueId(id128));
   return HSSB_OK;
+  });
 }
 
 int hssb_comm_init(hssb_matrix* h, const void* id128, int rank, int n_ranks) {
+  return guarded<int>([&]() -> int {
   if (!h || !id128) HSSB_FAIL(HSSB_ERR_ARG, "hssb_comm_init: NULL argument");
   if (n_ranks != h->n_shards || rank != h->shard_rank)
     HSSB_FAIL(HSSB_ERR_ARG, "hssb_comm_init: rank %d/%d does not match shard %d/%d", rank, n_ranks, h->shard_rank, h->n_shards);
@@ -1789,10 +1844,12 @@ int hssb_comm_init(hssb_matrix* h, const void* id128, int rank, int n_ranks) {
   HSSB_NCCL(g_nccl.CommInitRank(&comm, n_ranks, id, rank));
   h->nccl_comm = comm;
   return HSSB_OK;
+  });
 }
 
 
 int hssb_xchg_export(hssb_matrix* h, void* out128) {
+  return guarded<int>([&]() -> int {
   if (!h || !out128) HSSB_FAIL(HSSB_ERR_ARG, "hssb_xchg_export: NULL argument");
   if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle has no device");
   if (h->n_shards < 2 || h->n_shards > hssb_matrix::MAX_PEERS) HSSB_FAIL(HSSB_ERR_STATE, "hssb_xchg_export: needs 2..16 shards");
@@ -1811,9 +1868,11 @@ int hssb_xchg_export(hssb_matrix* h, void* out128) {
   memcpy((char*)out128 + 64, &hf, 64);
   h->xchg_exported = true;
   return HSSB_OK;
+  });
 }
 
 int hssb_xchg_import(hssb_matrix* h, const void* all_handles, int n_ranks) {
+  return guarded<int>([&]() -> int {
   if (!h || !all_handles) HSSB_FAIL(HSSB_ERR_ARG, "hssb_xchg_import: NULL argument");
   if (n_ranks != h->n_shards) HSSB_FAIL(HSSB_ERR_ARG, "hssb_xchg_import: %d handles for %d shards", n_ranks, h->n_shards);
   if (!h->xchg_exported) HSSB_FAIL(HSSB_ERR_STATE, "hssb_xchg_import: call hssb_xchg_export first");
@@ -1832,6 +1891,7 @@ int hssb_xchg_import(hssb_matrix* h, const void* all_handles, int n_ranks) {
   h->peer_xchg = true;
   invalidate_graphs(h);
   return HSSB_OK;
+  });
 }
 
 // ---- packed format on disk -------------------------------
@@ -1851,6 +1911,7 @@ static const uint32_t kFileVersion = 2;  // bump whenever layout_pool / stored_t
 static const uint32_t kNodeWords = 9;
 
 int hssb_save(const hssb_matrix* h, const char* path) {
+  return guarded<int>([&]() -> int {
   if (!h || !path) HSSB_FAIL(HSSB_ERR_ARG, "hssb_save: NULL argument");
   FILE* fp = fopen(path, "wb");
   if (!fp) HSSB_FAIL(HSSB_ERR_ARG, "hssb_save: cannot open %s for writing", path);
@@ -1881,10 +1942,12 @@ int hssb_save(const hssb_matrix* h, const char* path) {
   ok = (fclose(fp) == 0) && ok;
   if (!ok) HSSB_FAIL(HSSB_ERR_ARG, "hssb_save: write to %s failed", path);
   return HSSB_OK;
+  });
 }
 
 // device >= 0: load onto that GPU; device < 0: host-only (plan-only) handle for CPU-side inspection.
 int hssb_load(const char* path, int device, hssb_matrix** out) {
+  return guarded<int>([&]() -> int {
   if (!path || !out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: NULL argument");
   *out = nullptr;
   if (device >= 0) { int rc = check_device(device); if (rc) return rc; }
@@ -1894,21 +1957,45 @@ int hssb_load(const char* path, int device, hssb_matrix** out) {
   FileHeader hd;
   if (fread(&hd, sizeof(hd), 1, fp) != 1 || memcmp(hd.magic, kMagic, 8) != 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: %s is not an hssb200 file", path);
   if (hd.version != kFileVersion || hd.node_words != kNodeWords) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: file version %u, library reads %u", hd.version, kFileVersion);
-  if (hd.n_nodes <= 0 || hd.pool_len <= 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: corrupt header");
+  // The file is untrusted input: every size is checked against the file length before anything is allocated, and
+  // the node table must be a proper tree in BFS order (children of the k-th branch are nodes 2k+1, 2k+2 of the
+  // branch sequence: consecutive, after their parent, each referenced exactly once) -- a cycle would send the
+  // planner's tree walks into an endless loop.
+  if (hd.n_nodes <= 0 || hd.pool_len <= 0 || hd.n_nodes > (int64_t)1 << 40 || hd.pool_len > (int64_t)1 << 48)
+    HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: corrupt header");
+  if (hd.n_shards < 1 || hd.n_shards > hssb_matrix::MAX_PEERS || !is_pow2(hd.n_shards) || hd.shard_rank < 0 || hd.shard_rank >= hd.n_shards)
+    HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: corrupt header (shard %d of %d)", hd.shard_rank, hd.n_shards);
+  {
+    const long pos = ftell(fp);
+    if (pos < 0 || fseek(fp, 0, SEEK_END) != 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: cannot seek in %s", path);
+    const long fsize = ftell(fp);
+    if (fseek(fp, pos, SEEK_SET) != 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: cannot seek in %s", path);
+    const double need = (double)pos + (double)hd.n_nodes * kNodeWords * 8.0 + (double)hd.pool_len * 8.0;
+    if ((double)fsize < need) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: file is truncated (%ld bytes, header asks for %.0f)", fsize, need);
+  }
   std::unique_ptr<hssb_matrix> H(new (std::nothrow) hssb_matrix());
   if (!H) HSSB_FAIL(HSSB_ERR_ALLOC, "hssb_load: out of memory");
   H->device = device < 0 ? -1 : device;
   H->shard_rank = hd.shard_rank; H->n_shards = hd.n_shards;
   H->synthetic = hd.synthetic != 0; H->seed = hd.seed; H->synth_rank = hd.synth_rank;
   H->nodes.resize((size_t)hd.n_nodes);
+  int64_t next_child = 1;
   for (Node& t : H->nodes) {
     int64_t w[kNodeWords];
     if (fread(w, sizeof(int64_t), kNodeWords, fp) != kNodeWords) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: file is truncated");
     t.left = w[0]; t.right = w[1]; t.leaf = w[2] != 0; t.remote = w[3] != 0;
     t.m = w[4]; t.n = w[5]; t.kr = w[6]; t.kw = w[7]; t.heap_id = (uint64_t)w[8];
-    if ((!t.leaf && !t.remote) && (t.left <= 0 || t.right <= 0 || t.left >= hd.n_nodes || t.right >= hd.n_nodes))
-      HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: corrupt node table");
+    if (t.m < 0 || t.n < 0 || t.kr < 0 || t.kw < 0 || t.m > (int64_t)1 << 40 || t.n > (int64_t)1 << 40 || t.kr > INT32_MAX || t.kw > INT32_MAX)
+      HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: corrupt node table (sizes)");
+    if (!t.leaf && !t.remote) {
+      if (t.left != next_child || t.right != next_child + 1 || t.right >= hd.n_nodes)
+        HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: corrupt node table (not a tree in breadth-first order)");
+      next_child += 2;
+    } else {
+      t.left = t.right = -1;
+    }
   }
+  if (next_child != hd.n_nodes) HSSB_FAIL(HSSB_ERR_ARG, "hssb_load: corrupt node table (%lld nodes, %lld reachable)", (long long)hd.n_nodes, (long long)next_child);
   int rc;
   if (device < 0) {
     rc = plan_matrix(H.get());
@@ -1932,10 +2019,12 @@ int hssb_load(const char* path, int device, hssb_matrix** out) {
   }
   *out = H.release();
   return HSSB_OK;
+  });
 }
 
 // ---- test hooks: host-only planning (no device required) --------------------
 int hssb_plan_only(hssb_builder* b, int64_t root, int shard_rank, int n_shards, hssb_matrix** out) {
+  return guarded<int>([&]() -> int {
   if (!b || !out) HSSB_FAIL(HSSB_ERR_ARG, "plan_only: NULL argument");
   *out = nullptr;
   if (root < 0 || root >= (int64_t)b->nodes.size()) HSSB_FAIL(HSSB_ERR_ARG, "plan_only: invalid root id");
@@ -1949,10 +2038,12 @@ int hssb_plan_only(hssb_builder* b, int64_t root, int shard_rank, int n_shards, 
   fill_pool_host(H.get(), &src);
   *out = H.release();
   return HSSB_OK;
+  });
 }
 
 int hssb_plan_only_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, int shard_rank, int n_shards,
                              hssb_matrix** out) {
+  return guarded<int>([&]() -> int {
   if (!out) HSSB_FAIL(HSSB_ERR_ARG, "plan_only_synthetic: out is NULL");
   *out = nullptr;
   if (n <= 0 || leafsize <= 0 || rank < 0) HSSB_FAIL(HSSB_ERR_ARG, "plan_only_synthetic: bad sizes");
@@ -1967,17 +2058,21 @@ int hssb_plan_only_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t
   fill_pool_host(H.get(), nullptr);
   *out = H.release();
   return HSSB_OK;
+  });
 }
 
 int hssb_debug_counts(const hssb_matrix* h, int64_t* n_tasks, int64_t* n_phases, int64_t* pool_len) {
+  return guarded<int>([&]() -> int {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_counts: NULL handle");
   if (n_tasks) *n_tasks = (int64_t)h->tasks_host.size();
   if (n_phases) *n_phases = (int64_t)(h->phases.size() + h->phases_t.size() + h->phases_u.size());  // forward, transposed, ULV solve
   if (pool_len) *pool_len = h->pool_len;
   return HSSB_OK;
+  });
 }
 
 int hssb_debug_task(const hssb_matrix* h, int64_t i, hssb_task_t* o) {
+  return guarded<int>([&]() -> int {
   if (!h || !o || i < 0 || i >= (int64_t)h->tasks_host.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_task: bad argument");
   const GTask& t = h->tasks_host[(size_t)i];
   o->a0 = t.a0; o->a1 = t.a1; o->b0 = t.b0; o->b1 = t.b1; o->c = t.c;
@@ -1985,9 +2080,11 @@ int hssb_debug_task(const hssb_matrix* h, int64_t i, hssb_task_t* o) {
   o->M = t.M; o->K0 = t.K0; o->K1 = t.K1; o->ta0 = t.ta0; o->ta1 = t.ta1;
   o->sb0 = t.sb0; o->sb1 = t.sb1; o->sc = t.sc; o->epilogue = t.epilogue;
   return HSSB_OK;
+  });
 }
 
 int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* o) {
+  return guarded<int>([&]() -> int {
   if (!h || !o || i < 0 || i >= (int64_t)(h->phases.size() + h->phases_t.size() + h->phases_u.size()))
     HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_phase: bad argument");
   const size_t nf = h->phases.size(), nt = h->phases_t.size();
@@ -1997,12 +2094,14 @@ int hssb_debug_phase(const hssb_matrix* h, int64_t i, hssb_phase_t* o) {
   o->top = p.top; o->fast = p.fast; o->transposed = which;
   o->xchg_zoff = h->xchg_zoff; o->xchg_slot_rows = h->xchg_slot_rows;
   return HSSB_OK;
+  });
 }
 
 // Per-step device time of the persistent tree kernel (single shard, diagnostics): launches the tree
 // kernel alone on the current workspace contents with CTA 0 recording its SM clock at every grid
 // barrier.  us_out[j] = microseconds of step j (j-th covered phase of the forward plan).
 int hssb_debug_tree_trace(hssb_matrix* h, int64_t nrhs, double* us_out, int cap) {
+  return guarded<int>([&]() -> int {
   if (!h || !us_out || nrhs <= 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_tree_trace: bad argument");
   if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle has no device");
   if (h->n_shards != 1) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_tree_trace: single-shard handles only");
@@ -2034,9 +2133,11 @@ int hssb_debug_tree_trace(hssb_matrix* h, int64_t nrhs, double* us_out, int cap)
   cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device);
   for (int j = 0; j < ns; ++j) us_out[j] = (double)(t[(size_t)j + 1] - t[(size_t)j]) / (khz * 1e-3);
   return ns;
+  });
 }
 
 int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len) {
+  return guarded<int>([&]() -> int {
   if (!h || !out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_pool: NULL argument");
   if (len < h->pool_len) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_pool: need %lld doubles", (long long)h->pool_len);
   if (!h->pool_host.empty()) { memcpy(out, h->pool_host.data(), (size_t)h->pool_len * 8); return HSSB_OK; }
@@ -2044,11 +2145,13 @@ int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len) {
   DeviceGuard dg(h->device);
   HSSB_CUDA(cudaMemcpy(out, h->pool_dev, (size_t)h->pool_len * 8, cudaMemcpyDeviceToHost));
   return HSSB_OK;
+  });
 }
 
 // Host image of the adjoint twin pool (what ensure_twin builds on the device), for plan-only and
 // device handles alike: CPU tests run the FORWARD plan over it and must obtain A' X.
 int hssb_debug_pool_t(const hssb_matrix* h, double* out, int64_t len) {
+  return guarded<int>([&]() -> int {
   if (!h || !out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_pool_t: NULL argument");
   if (len < h->pool_len) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_pool_t: need %lld doubles", (long long)h->pool_len);
   std::vector<TwinBlock> tb;
@@ -2064,20 +2167,24 @@ int hssb_debug_pool_t(const hssb_matrix* h, double* out, int64_t len) {
     for (int64_t c = 0; c < b.cols; ++c)
       for (int64_t r = 0; r < b.rows; ++r) out[b.dst + r * b.ld_dst + c] = h->pool_host[(size_t)(b.src + c * b.ld_src + r)];
   return HSSB_OK;
+  });
 }
 
 // ULV test hooks: factorise a plan-only handle on the HOST with the same node routine the device
 // kernel runs (single-thread team), and expose the factor pool so that the numpy plan interpreter can
 // run the solve's task table (phases with transposed == 2) over it.
 int hssb_debug_ulv_factor_host(hssb_matrix* h) {
+  return guarded<int>([&]() -> int {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_ulv_factor_host: NULL handle");
   if (h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_ulv_factor_host: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
   if (h->pool_host.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_ulv_factor_host: plan-only handles only");
   ulv_factor_host(h);
   return HSSB_OK;
+  });
 }
 
 int hssb_debug_ulv_pool(const hssb_matrix* h, double* out, int64_t len) {
+  return guarded<int>([&]() -> int {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_ulv_pool: NULL handle");
   if (h->ulv.empty() || !h->ulv_factored) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_ulv_pool: not factorised");
   if (!out || len < h->ulv_pool_len) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_ulv_pool: need %lld doubles", (long long)h->ulv_pool_len);
@@ -2085,6 +2192,7 @@ int hssb_debug_ulv_pool(const hssb_matrix* h, double* out, int64_t len) {
   DeviceGuard dg(h->device);
   HSSB_CUDA(cudaMemcpy(out, h->ulv_pool_dev, (size_t)h->ulv_pool_len * 8, cudaMemcpyDeviceToHost));
   return HSSB_OK;
+  });
 }
 
 }  // extern "C"

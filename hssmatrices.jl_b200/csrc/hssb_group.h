@@ -192,6 +192,7 @@ extern "C" {
 
 int hssb_group_create_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint64_t seed, const int* devices, int n_devices,
                                 hssb_group** out) {
+  return guarded<int>([&]() -> int {
   if (!out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_group_create_synthetic: out is NULL");
   *out = nullptr;
   if (int rc = group_devices_ok(devices, n_devices, "hssb_group_create_synthetic")) return rc;
@@ -206,9 +207,11 @@ int hssb_group_create_synthetic(int64_t n, int64_t leafsize, int64_t rank, uint6
   const int rc = group_wire(g, out);
   if (rc) hssb_group_destroy(g.release());
   return rc;
+  });
 }
 
 int hssb_group_finalize(hssb_builder* b, int64_t root, const int* devices, int n_devices, hssb_group** out) {
+  return guarded<int>([&]() -> int {
   if (!out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_group_finalize: out is NULL");
   *out = nullptr;
   if (int rc = group_devices_ok(devices, n_devices, "hssb_group_finalize")) return rc;
@@ -223,9 +226,11 @@ int hssb_group_finalize(hssb_builder* b, int64_t root, const int* devices, int n
   const int rc = group_wire(g, out);
   if (rc) hssb_group_destroy(g.release());
   return rc;
+  });
 }
 
 int hssb_group_destroy(hssb_group* g) {
+  return guarded<int>([&]() -> int {
   if (!g) return HSSB_OK;
   // quiesce every device before any workspace a peer may still be writing to goes away
   for (hssb_matrix* h : g->shard)
@@ -236,6 +241,7 @@ int hssb_group_destroy(hssb_group* g) {
   for (hssb_matrix* h : g->shard) hssb_destroy(h);
   delete g;
   return HSSB_OK;
+  });
 }
 
 int hssb_group_size(const hssb_group* g) { return g ? (int)g->shard.size() : 0; }
@@ -246,32 +252,42 @@ hssb_matrix* hssb_group_shard(hssb_group* g, int i) {
 }
 
 int hssb_group_reserve(hssb_group* g, int64_t max_nrhs) {
+  return guarded<int>([&]() -> int {
   if (int rc = group_check(g, "hssb_group_reserve")) return rc;
   if (max_nrhs < 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_group_reserve: bad argument");
   if (g->shard.size() == 1) return hssb_reserve(g->shard[0], max_nrhs);
   return group_prepare(g, max_nrhs);
+  });
 }
 
 int hssb_group_matmul(hssb_group* g, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx, double* Y, int64_t ldy,
                       double alpha, double beta) {
-  return group_host(g, 0, rows_y, rows_x, nrhs, X, ldx, Y, ldy, alpha, beta);
+  return guarded<int>([&]() -> int {
+    return group_host(g, 0, rows_y, rows_x, nrhs, X, ldx, Y, ldy, alpha, beta);
+  });
 }
 
 int hssb_group_matmul_t(hssb_group* g, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx, double* Y,
                         int64_t ldy, double alpha, double beta) {
-  return group_host(g, 1, rows_y, rows_x, nrhs, X, ldx, Y, ldy, alpha, beta);
+  return guarded<int>([&]() -> int {
+    return group_host(g, 1, rows_y, rows_x, nrhs, X, ldx, Y, ldy, alpha, beta);
+  });
 }
 
 int hssb_group_matmul_dev(hssb_group* g, int64_t nrhs, const double* const* dX, int64_t ldx, double* const* dY, int64_t ldy, double alpha,
                           double beta, void* const* streams) {
-  return group_dev(g, 0, nrhs, dX, ldx, dY, ldy, alpha, beta, streams);
+  return guarded<int>([&]() -> int {
+    return group_dev(g, 0, nrhs, dX, ldx, dY, ldy, alpha, beta, streams);
+  });
 }
 
 int hssb_group_sync(hssb_group* g) {
+  return guarded<int>([&]() -> int {
   if (int rc = group_check(g, "hssb_group_sync")) return rc;
   for (hssb_matrix* h : g->shard)
     if (int rc = hssb_sync(h)) return rc;
   return HSSB_OK;
+  });
 }
 
 }  // extern "C"

@@ -150,7 +150,15 @@ int hssb_matmul(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
                 const double* X, int64_t ldx, double* Y, int64_t ldy, double alpha, double beta);
 
 /* Same with DEVICE pointers, asynchronous on `stream` (a cudaStream_t; NULL =
- * the CUDA default stream).  This is the timed entry.                        */
+ * the CUDA default stream).  This is the timed entry.
+ * CONTRACT for every *_dev entry (product, transposed product, solve): a handle owns ONE set of Z / F
+ * workspaces, one task table and one graph cache, so
+ *   - calls on one handle must be ordered: issue them on one stream, or make the next call's stream wait
+ *     for the previous call (event) -- two calls in flight on different streams race on the workspaces;
+ *   - a call with more right-hand sides than any before it (or the first transposed product / solve) may
+ *     reallocate workspaces: let earlier asynchronous calls finish first (hssb_reserve up front avoids it);
+ *   - X and Y (B and Z for the solve) must not overlap: the leaf phases read X while they write Y.
+ * One handle = one owner thread at a time; different handles are independent.            */
 int hssb_matmul_dev(hssb_matrix* h, int64_t rows_y, int64_t rows_x, int64_t nrhs,
                     const double* dX, int64_t ldx, double* dY, int64_t ldy, double alpha, double beta,
                     void* stream);

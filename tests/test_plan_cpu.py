@@ -282,6 +282,25 @@ def test_save_load_roundtrip(hb, oracle, tmp_path):
     Y = np.zeros((300, 3), order="F")
     plan_interp.run_plan(Q, X, Y)
     assert relerr(Y, oracle.matmul(h, X)) <= TOL
+    # the file is untrusted input: a node table that is not a tree (here: a node that is its own child, which would
+    # send the planner's walks into an endless loop), absurd sizes or a bad shard header are rejected
+    import struct
+    raw = open(f, "rb").read()
+    hdr = struct.calcsize("<8sIIqqiiiiQq")
+    assert raw[:7] == b"HSSB200"
+
+    def damaged(off, fmt, value, name):
+        g = str(tmp_path / name)
+        with open(g, "wb") as fh:
+            fh.write(raw[:off] + struct.pack(fmt, value) + raw[off + struct.calcsize(fmt):])
+        with pytest.raises(hb.HssbError):
+            hb.load(g, device=-1)
+
+    damaged(hdr, "<q", 0, "selfloop.hssb")                 # root.left = 0: a cycle
+    damaged(hdr + 8, "<q", 1, "shared.hssb")               # root.right = root.left: a node referenced twice
+    damaged(hdr + 4 * 8, "<q", -5, "negsize.hssb")         # root.m < 0
+    damaged(16, "<q", 1 << 50, "hugenodes.hssb")           # n_nodes far beyond the file length
+    damaged(32, "<i", 7, "badshard.hssb")                  # shard_rank 7 of 1
     with open(f, "r+b") as fh:      # a damaged file must be rejected, not half-loaded
         fh.truncate(200)
     with pytest.raises(hb.HssbError):
