@@ -35,6 +35,10 @@ class HssbError(RuntimeError):
     """Any failure reported by libhssb200 other than a dimension mismatch."""
 
 
+class SingularException(ArithmeticError):
+    """Julia's LinearAlgebra.SingularException (ulvfactor.jl:83 `D \\ b` on a singular reduced block): HSSB_ERR_SINGULAR."""
+
+
 class DimensionMismatch(ValueError):
     """Julia's DimensionMismatch (src/matmul.jl:19-20, src/hssmatrix.jl:58-59)."""
 
@@ -165,6 +169,8 @@ def _check(rc):
     msg = lib().hssb_last_error().decode("utf-8", "replace")
     if rc == -2:
         raise DimensionMismatch(msg)
+    if rc == -7:
+        raise SingularException(msg)
     raise HssbError(f"hssb200 error {rc}: {msg}")
 
 

@@ -2178,7 +2178,7 @@ int hssb_debug_ulv_factor_host(hssb_matrix* h) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_ulv_factor_host: NULL handle");
   if (h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_ulv_factor_host: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
   if (h->pool_host.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_ulv_factor_host: plan-only handles only");
-  ulv_factor_host(h);
+  if (int rc = ulv_factor_host(h)) return rc;
   return HSSB_OK;
   });
 }

@@ -160,7 +160,7 @@ struct hssb_matrix {
   double* ulv_pool_dev = nullptr;
   std::vector<double> ulv_pool_host;  // plan-only handles: factorised on the host by the test hook
   bool ulv_factored = false;
-  bool ulv_fast_form = false;         // HSSB_OPT_ULV_FAST requested
+  bool ulv_fast_form = true;          // HSSB_OPT_ULV_FAST (default on since it ran green on hardware: solve 2.60 -> 1.79 ms on config 3)
   bool ulv_ff = false;                // ... and the tree qualifies: the ULV plan is in fast form
   int64_t ulv_task0 = -1;             // first ULV task in tasks_host (the ULV plan can be rebuilt)
   std::vector<hssb::GTask> tasks_host;

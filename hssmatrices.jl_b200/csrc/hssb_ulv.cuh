@@ -204,8 +204,24 @@ struct UlvCtx {
   const double* pool;  // primary generator pool
   double* fpool;       // factor pool (output)
   double* red;         // reduced generators of every node (input from the children, output for the parent)
-  int32_t MI, NI, KR, KW;  // maxima over the nodes: scratch sizing
+  int32_t MI, NI, KR, KW;  // maxima over the nodes of this launch (one tree level): scratch sizing
+  double* pivmin;      // per node: smallest |pivot| the node divides by (+inf if it eliminates nothing); may be NULL
 };
+
+// The factorisation divides by the diagonal of a triangular factor twice: L1 (ulvfactor.jl:48, trsm) and the
+// root block (ulvfactor.jl:83, D \ b).  A zero (or non-finite) pivot is recorded here and turned into
+// HSSB_ERR_SINGULAR by the caller, like the SingularException the reference throws.
+HSSB_HD void ulv_record_pivot(const Team& tm, const UlvCtx& cx, int node, Mat Tri, int n) {
+  if (cx.pivmin && tm.tid == 0) {
+    double mn = INFINITY;
+    for (int i = 0; i < n; ++i) {
+      double a = fabs(Tri(i, i));
+      if (!(a >= 0.0) || a == INFINITY) a = 0.0;  // NaN / Inf count as a breakdown
+      mn = a < mn ? a : mn;
+    }
+    cx.pivmin[node] = mn;
+  }
+}
 
 // doubles of scratch one team needs
 HSSB_HD int64_t ulv_scratch_len(int64_t MI, int64_t NI, int64_t KR, int64_t KW) {
@@ -284,6 +300,7 @@ HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double*
   if (u.is_root) {
     tm_eye(tm, Q, m, m, 1.0);
     tm_qr(tm, Din, m, n, Q, m);
+    ulv_record_pivot(tm, cx, node, Din, n);
     tm_trsm_upper(tm, Din, n, Q, m);  // Q <- R^-1 Q' = D^-1 (n x m, m == n)
     if (u.is_leaf) {
       tm_copy(tm, colmajor(cx.fpool + u.ac[0], u.ld_ac), Q, n, m);
@@ -305,6 +322,7 @@ HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double*
     tm_gemm(tm, L2, Dbot, P.t(), k, n, n, 1.0, 0.0);             // L2 = Dbot P'
     tm_gemm(tm, Vq, P, Vin, n, kw, n, 1.0, 0.0);                 // Vq = P V
     tm_copy(tm, T1, Q.sub(k, 0), mk, m);                         // Qtop
+    ulv_record_pivot(tm, cx, node, Dtop, mk);
     tm_trsm_lower(tm, Dtop, mk, T1, m);                          // T1 = L1^-1 Qtop
     tm_copy(tm, T23, Q, k, m);                                   // Qbot
     tm_gemm(tm, T23, L2, T1, k, m, mk, -1.0, 1.0);               // T2 = Qbot - L2a T1
@@ -324,6 +342,7 @@ HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double*
       }
     }
   } else {  // cannot be compressed (ulvfactor.jl:31-37): everything is handed to the parent
+    ulv_record_pivot(tm, cx, node, Din, 0);
     tm_eye(tm, T23, k, m, 1.0);
     tm_eye(tm, T23.sub(k, 0), kw, m, 0.0);
     tm_copy(tm, colmajor(cx.red + u.rD, k > 0 ? k : 1), Din, k, no);

@@ -290,19 +290,49 @@ static std::vector<std::vector<int32_t>> ulv_levels(const hssb_matrix* H) {
   return lv;
 }
 
+// Scratch maxima over the nodes of one level (ulv_scratch_len is sized per launch, not for the whole tree: in a
+// tree whose upper nodes are much larger than its leaves -- ranks close to the block size -- a leaf level
+// thousands of nodes wide must not be charged hundreds of copies of the root-sized scratch).
+struct UlvLevelDims { int32_t MI = 1, NI = 1, KR = 1, KW = 1; };
+static UlvLevelDims ulv_level_dims(const hssb_matrix* H, const std::vector<int32_t>& level) {
+  UlvLevelDims d;
+  for (int32_t i : level) {
+    const UlvNode& u = H->ulv[(size_t)i];
+    d.MI = std::max(d.MI, u.m_in); d.NI = std::max(d.NI, u.n_in);
+    d.KR = std::max(d.KR, std::max(u.kr, std::max(u.kr1, u.kr2)));
+    d.KW = std::max(d.KW, std::max(u.kw, std::max(u.kw1, u.kw2)));
+  }
+  return d;
+}
+
+// First node whose factorisation divided by a zero or non-finite pivot, -1 if none.
+static int64_t ulv_first_breakdown(const std::vector<double>& pivmin) {
+  for (size_t i = 0; i < pivmin.size(); ++i)
+    if (!(pivmin[i] > 0.0)) return (int64_t)i;
+  return -1;
+}
+
 // Host instantiation of the factorisation (single-thread team) for plan-only handles: CPU tests only.
-static void ulv_factor_host(hssb_matrix* H) {
+static int ulv_factor_host(hssb_matrix* H) {
   H->ulv_pool_host.assign((size_t)H->ulv_pool_len, 0.0);
+  H->ulv_factored = false;
   std::vector<double> red((size_t)H->ulv_red_len, 0.0);
-  std::vector<double> scratch((size_t)ulv_scratch_len(H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW), 0.0);
-  UlvCtx cx{H->ulv.data(), H->pool_host.data(), H->ulv_pool_host.data(), red.data(), H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW};
+  std::vector<double> pivmin(H->nodes.size(), INFINITY);
   const Team tm{0, 1};
-  for (auto& level : ulv_levels(H))
+  for (auto& level : ulv_levels(H)) {
+    const UlvLevelDims d = ulv_level_dims(H, level);
+    std::vector<double> scratch((size_t)ulv_scratch_len(d.MI, d.NI, d.KR, d.KW), 0.0);
+    UlvCtx cx{H->ulv.data(), H->pool_host.data(), H->ulv_pool_host.data(), red.data(), d.MI, d.NI, d.KR, d.KW, pivmin.data()};
     for (int32_t node : level) {
       if (H->ulv_ff) ulv_factor_node<true>(tm, cx, node, scratch.data());
       else ulv_factor_node<false>(tm, cx, node, scratch.data());
     }
+  }
+  const int64_t bad = ulv_first_breakdown(pivmin);
+  if (bad >= 0)
+    HSSB_FAIL(HSSB_ERR_SINGULAR, "SingularException: the ULV factorisation met a zero pivot at node %lld (ulvfactor.jl:48 / :83)", (long long)bad);
   H->ulv_factored = true;
+  return HSSB_OK;
 }
 
 // Device factorisation: one launch per tree level, one CTA per node.
@@ -316,45 +346,65 @@ static int ulv_factor_device(hssb_matrix* H) {
     HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of the %.3f GB ULV factor pool failed", pool_b * 1e-9);
   }
   const auto levels = ulv_levels(H);
-  size_t widest = 1;
-  for (auto& l : levels) widest = std::max(widest, l.size());
-  const int64_t stride = round_up(ulv_scratch_len(H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW), 16);
-  // CTAs in flight: three per SM (80 registers x 256 threads), fewer when the scratch of large nodes would not fit in 8 GiB
-  int ctas = (int)std::min<size_t>(widest, 148 * 3);
-  while (ctas > 1 && (size_t)ctas * (size_t)stride * 8 > ((size_t)8 << 30)) ctas /= 2;
+  // per level: scratch per CTA and CTAs in flight (three per SM: 80 registers x 256 threads; fewer when the
+  // scratch of large nodes would not fit in 8 GiB)
+  struct LevelRun { UlvLevelDims d; int64_t stride; int ctas; };
+  std::vector<LevelRun> runs;
+  size_t scratch_doubles = 1;
+  for (auto& l : levels) {
+    LevelRun r;
+    r.d = ulv_level_dims(H, l);
+    r.stride = round_up(ulv_scratch_len(r.d.MI, r.d.NI, r.d.KR, r.d.KW), 16);
+    r.ctas = (int)std::min<size_t>(std::max<size_t>(l.size(), 1), 148 * 3);
+    while (r.ctas > 1 && (size_t)r.ctas * (size_t)r.stride * 8 > ((size_t)8 << 30)) r.ctas /= 2;
+    scratch_doubles = std::max(scratch_doubles, (size_t)r.ctas * (size_t)r.stride);
+    runs.push_back(r);
+  }
   UlvNode* d_nodes = nullptr;
   int32_t* d_list = nullptr;
-  double *d_red = nullptr, *d_scratch = nullptr;
-  auto cleanup = [&]() { cudaFree(d_nodes); cudaFree(d_list); cudaFree(d_red); cudaFree(d_scratch); };
+  double *d_red = nullptr, *d_scratch = nullptr, *d_piv = nullptr;
+  auto cleanup = [&]() { cudaFree(d_nodes); cudaFree(d_list); cudaFree(d_red); cudaFree(d_scratch); cudaFree(d_piv); };
+  std::vector<double> pivmin(H->nodes.size(), INFINITY);
   cudaError_t e = cudaMalloc(&d_nodes, H->ulv.size() * sizeof(UlvNode));
   if (e == cudaSuccess) e = cudaMalloc(&d_list, H->nodes.size() * sizeof(int32_t));
   if (e == cudaSuccess) e = cudaMalloc(&d_red, (size_t)H->ulv_red_len * sizeof(double));
-  if (e == cudaSuccess) e = cudaMalloc(&d_scratch, (size_t)ctas * (size_t)stride * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_scratch, scratch_doubles * sizeof(double));
+  if (e == cudaSuccess) e = cudaMalloc(&d_piv, pivmin.size() * sizeof(double));
   if (e == cudaSuccess) e = cudaMemsetAsync(H->ulv_pool_dev, 0, pool_b, H->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_nodes, H->ulv.data(), H->ulv.size() * sizeof(UlvNode), cudaMemcpyHostToDevice, H->stream);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_piv, pivmin.data(), pivmin.size() * sizeof(double), cudaMemcpyHostToDevice, H->stream);
   std::vector<int32_t> flat;
   for (auto& l : levels) flat.insert(flat.end(), l.begin(), l.end());
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_list, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, H->stream);
   if (e == cudaSuccess) {
-    UlvCtx cx{d_nodes, H->pool_dev, H->ulv_pool_dev, d_red, H->ulv_MI, H->ulv_NI, H->ulv_KR, H->ulv_KW};
     size_t at = 0;
-    for (auto& l : levels) {
+    for (size_t li = 0; li < levels.size(); ++li) {
+      const auto& l = levels[li];
+      const LevelRun& r = runs[li];
       if (!l.empty()) {
-        const int grid = (int)std::min<size_t>(l.size(), (size_t)ctas);
-        if (H->ulv_ff) ulv_factor_kernel_ff<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, stride);
-        else ulv_factor_kernel<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, stride);
+        UlvCtx cx{d_nodes, H->pool_dev, H->ulv_pool_dev, d_red, r.d.MI, r.d.NI, r.d.KR, r.d.KW, d_piv};
+        const int grid = (int)std::min<size_t>(l.size(), (size_t)r.ctas);
+        if (H->ulv_ff) ulv_factor_kernel_ff<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, r.stride);
+        else ulv_factor_kernel<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, r.stride);
         H->launches++;
       }
       at += l.size();
     }
     e = cudaGetLastError();
   }
+  if (e == cudaSuccess) e = cudaMemcpyAsync(pivmin.data(), d_piv, pivmin.size() * sizeof(double), cudaMemcpyDeviceToHost, H->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(H->stream);
   cleanup();
   if (e != cudaSuccess) {
     cudaFree(H->ulv_pool_dev);
     H->ulv_pool_dev = nullptr;
     HSSB_FAIL(HSSB_ERR_CUDA, "ULV factorisation failed: %s", cudaGetErrorString(e));
+  }
+  const int64_t bad = ulv_first_breakdown(pivmin);
+  if (bad >= 0) {  // do not keep (or cache) factors full of Inf / NaN
+    cudaFree(H->ulv_pool_dev);
+    H->ulv_pool_dev = nullptr;
+    HSSB_FAIL(HSSB_ERR_SINGULAR, "SingularException: the ULV factorisation met a zero pivot at node %lld (ulvfactor.jl:48 / :83)", (long long)bad);
   }
   H->ulv_factored = true;
   return HSSB_OK;

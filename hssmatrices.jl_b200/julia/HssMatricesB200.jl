@@ -27,6 +27,7 @@ function check(rc::Integer)
   rc >= 0 && return rc
   msg = unsafe_string(ccall((:hssb_last_error, libhssb), Cstring, ()))
   rc == -2 && throw(DimensionMismatch(msg))   # same exception type as src/matmul.jl:19-20
+  rc == -7 && throw(SingularException(0))     # what `D \ b` throws at src/ulvfactor.jl:83
   throw(HssbError(Cint(rc), msg))
 end
 

@@ -36,7 +36,8 @@ typedef enum hssb_status {
   HSSB_ERR_CUDA = -3,     /* CUDA runtime error or no usable device                    */
   HSSB_ERR_ALLOC = -4,    /* host or device allocation failed                          */
   HSSB_ERR_STATE = -5,    /* call not valid in this state (e.g. comm not initialised)  */
-  HSSB_ERR_COMM = -6      /* NCCL error / NCCL not loadable                            */
+  HSSB_ERR_COMM = -6,     /* NCCL error / NCCL not loadable                            */
+  HSSB_ERR_SINGULAR = -7  /* Julia SingularException: hssb_ulv_factor / hssb_solve met a zero pivot (ulvfactor.jl:48, :83) */
 } hssb_status;
 
 typedef struct hssb_builder hssb_builder; /* host-side packer front end */

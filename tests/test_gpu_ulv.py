@@ -131,3 +131,29 @@ def test_solver_errors(gpu, oracle):
     with gpu.synthetic(2048, 128, 32, 1) as S:
         with pytest.raises(gpu.DimensionMismatch):
             S.solve(np.zeros((2047, 2)))
+
+
+def test_singular_matrix_on_device(gpu, oracle):
+    """A zero pivot in the device factorisation surfaces as SingularException (HSSB_ERR_SINGULAR), like `D \\ b` at
+    ulvfactor.jl:83; no factors are cached, and the product of the same handle keeps working."""
+    rng = np.random.default_rng(4)
+    cl = oracle.bisection_cluster(256, 32)
+    h = oracle.random_hss(cl, cl, rng, 2, 5)
+
+    def zero_d(t):
+        if t.leafnode:
+            t.D[...] = 0.0
+            t.U[...] = 0.0
+        else:
+            zero_d(t.A11)
+            zero_d(t.A22)
+
+    zero_d(h)   # A = 0: every reduced block is singular
+    X = rng.standard_normal((256, 3))
+    with gpu.pack(to_product_tree(gpu, h)) as P:
+        with pytest.raises(gpu.SingularException):
+            P.solve(X)
+        assert P.ulv_info.factored == 0
+        with pytest.raises(gpu.SingularException):
+            P.ulv_factor()
+        assert np.linalg.norm(P @ X) == 0.0

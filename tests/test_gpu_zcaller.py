@@ -70,19 +70,19 @@ def test_solve_golden_fixtures(hb, oracle):
         assert np.linalg.norm(got - z["Z"]) <= 1e-13 * float(z["cond"]) * np.linalg.norm(z["Z"]), f
 
 
-@pytest.mark.skipif(os.environ.get("HSSB_TEST_ULV_FAST") != "1",
-                    reason="experimental HSSB_OPT_ULV_FAST: fixed-shape kernels on the solve plan, not yet run on a GPU "
-                           "(set HSSB_TEST_ULV_FAST=1)")
 def test_ulv_fast_form_on_device(hb, oracle):
+    """The ULV solve of a uniform tree on the product's fixed-shape kernels (HSSB_OPT_ULV_FAST, the default) against
+    the general form on the any-shape kernel (option 0) and against the dense matrix."""
     if hb.device_count() == 0:
-        pytest.skip("no B200 visible")
+        pytest.fail("no B200 visible: the gpu-marked tests need the real device (no CPU fallback)")
     for n, ls, r, k in ((4096, 128, 32, 64), (4096, 128, 16, 20), (4096, 256, 32, 32)):
         with hb.synthetic(n, ls, r, 5) as P:
             B = oracle.synth_x(5, n, k)
-            Z0 = P.solve(B)
-            P.set_option(hb.OPT_ULV_FAST, 1)
             assert P.get_option(hb.OPT_ULV_FAST) == 2
             Z1 = P.solve(B)
+            P.set_option(hb.OPT_ULV_FAST, 0)
+            assert P.get_option(hb.OPT_ULV_FAST) == 0
+            Z0 = P.solve(B)
             assert np.linalg.norm(Z1 - Z0) <= 1e-9 * np.linalg.norm(Z0)
             R = P @ Z1 - B
             A = oracle.full(oracle.synthetic_hss(n, ls, r, 5))

@@ -244,20 +244,25 @@ def test_solve_golden_fixtures(hb, oracle, ulv_oracle):
 
 @pytest.mark.parametrize("n,ls,r", [(2048, 128, 16), (2048, 128, 32), (4096, 256, 32), (1024, 128, 64)])
 def test_ulv_fast_form_plan(hb, oracle, ulv_oracle, n, ls, r):
-    """HSSB_OPT_ULV_FAST (experimental): the solve plan of a uniform tree rebuilt in the shapes / padding of the
-    product's blocks.  Same solution as the default form; the phases a fixed-shape kernel can take are tagged
-    (leaf-up as V'-like 2r x m, square 2r x 2r merges, r x r top-down steps, leaf-down as D/U-like); fewer
-    flops (zloc is folded into the leaf output operator); switching back restores the default plan bit for bit."""
+    """HSSB_OPT_ULV_FAST (default on; it qualifies on uniform trees): the solve plan in the shapes / padding of the
+    product's blocks.  Same solution as the general form (option 0); the phases a fixed-shape kernel can take are
+    tagged (leaf-up as V'-like 2r x m, square 2r x 2r merges, r x r top-down steps, leaf-down as D/U-like); fewer
+    flops (zloc is folded into the leaf output operator); switching back and forth restores each plan bit for bit."""
     seed = 4
     h = oracle.synthetic_hss(n, ls, r, seed)
     B = oracle.synth_x(seed, n, 3)
     ref = ulv_oracle.ulvfactsolve(h, B)
     P = hb.synthetic(n, ls, r, seed, plan_only=True)
+    assert P.get_option(hb.OPT_ULV_FAST) == 2
+    Zf = solve_by_plan(P, B)
+    P.set_option(hb.OPT_ULV_FAST, 0)
+    assert P.get_option(hb.OPT_ULV_FAST) == 0
     Z0 = solve_by_plan(P, B)
     info0 = (P.ulv_info.flops_per_rhs, P.ulv_info.pool_bytes)
     P.set_option(hb.OPT_ULV_FAST, 1)
     assert P.get_option(hb.OPT_ULV_FAST) == 2 and P.ulv_info.factored == 0
     Z1 = solve_by_plan(P, B)
+    assert np.array_equal(Z1, Zf)
     tol = 1e-10 * np.linalg.norm(ref)   # these seeded matrices have cond ~ 1e5..1e6; measured 3e-13..5e-13
     assert np.linalg.norm(Z0 - ref) <= tol and np.linalg.norm(Z1 - ref) <= tol
     assert P.ulv_info.flops_per_rhs <= info0[0]
@@ -280,3 +285,41 @@ def test_ulv_fast_form_needs_uniform_tree(hb, oracle):
     B = rng.standard_normal((300, 2))
     Z = solve_by_plan(P, B)
     assert np.isfinite(Z).all()
+
+
+def test_singular_matrix_is_reported(hb, oracle):
+    """The reference throws SingularException from `D \\ b` (ulvfactor.jl:83) and from the trsm of :48 when a reduced
+    block is singular; the library records the pivots its factorisation divides by and returns
+    HSSB_ERR_SINGULAR instead of caching factors full of Inf / NaN."""
+    rng = np.random.default_rng(3)
+    # (1) the root is a leaf and its D is singular (two equal rows)
+    D = rng.standard_normal((40, 40))
+    D[7] = D[3]
+    D[:, 9] = 0.0
+    leafroot = hb.HssMatrix.leaf(D, np.zeros((40, 0)), np.zeros((40, 0)), rootnode=True)
+    P = hb.pack(leafroot, plan_only=True)
+    with pytest.raises(hb.SingularException):
+        P.debug_ulv_pool(factor_on_host=True)
+    assert P.ulv_info.factored == 0
+    # (2) a two-level tree whose reduced root block is exactly zero: all generators zero
+    cl = oracle.bisection_cluster(128, 32)
+    h = oracle.random_hss(cl, cl, rng, 2, 4)
+
+    def zero(t):
+        for f in ("D", "U", "V", "B12", "B21", "R1", "R2", "W1", "W2"):
+            a = getattr(t, f, None)
+            if isinstance(a, np.ndarray):
+                a[...] = 0.0
+        if not t.leafnode:
+            zero(t.A11)
+            zero(t.A22)
+
+    zero(h)
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    with pytest.raises(hb.SingularException):
+        P.debug_ulv_pool(factor_on_host=True)
+    # (3) a regular matrix still factorises
+    h = shifted(oracle, oracle.random_hss(cl, cl, rng, 2, 4), 10.0)
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    P.debug_ulv_pool(factor_on_host=True)
+    assert P.ulv_info.factored == 1
