@@ -446,6 +446,79 @@ def run_extra(ctx, name, steps, warmup, peaks):
         return {"error": repr(e)} if ctx["rank"] == 0 else None
 
 
+def run_small_tree_extra(ctx, what, n, leaf, rmin, rmax, k, steps, peaks):
+    """BASELINE configs 1-2 are matrices out of a compression: ragged leaves, per-node ranks (9-20), far smaller
+    than L2.  What the product costs depends only on the tree's shapes, so this times a tree of THOSE shapes
+    (clustertree.jl:27-35 bisection, ranks drawn per node, random generators, registered node by node through the
+    builder like any caller's HssMatrix) -- the Cauchy matrices themselves need the compression restatement,
+    which lives in oracle/ and is only used by the tests (tests/test_gpu_parity.py runs them against the
+    oracle).  L2 is flushed between timed products (the whole problem fits in it).  The check printed is the
+    dataflow kernel against the level-by-level launches of the same plan (identical tiles: bit for bit)."""
+    hb, torch = ctx["hb"], ctx["torch"]
+    try:
+        import numpy as np
+        rng = np.random.default_rng(SEED)
+
+        def build(lo, hi, isroot):
+            m = hi - lo
+            if m <= leaf:
+                kk = 0 if isroot else int(rng.integers(rmin, rmax + 1))
+                return hb.HssMatrix.leaf(rng.standard_normal((m, m)), rng.standard_normal((m, kk)), rng.standard_normal((m, kk)), rootnode=isroot)
+            mid = lo + (m + 1) // 2
+            a, b = build(lo, mid, False), build(mid, hi, False)
+            (kr1, kw1), (kr2, kw2) = hb.gensize(a), hb.gensize(b)
+            kk = 0 if isroot else int(rng.integers(rmin, rmax + 1))
+            sc = 1.0 / np.sqrt(2.0 * max(kk, 1))
+            return hb.HssMatrix.branch(a, b, rng.standard_normal((kr1, kw2)), rng.standard_normal((kr2, kw1)),
+                                       sc * rng.standard_normal((kr1, kk)), sc * rng.standard_normal((kw1, kk)),
+                                       sc * rng.standard_normal((kr2, kk)), sc * rng.standard_normal((kw2, kk)), rootnode=isroot)
+
+        P = hb.pack(build(0, n, True), device=ctx["local"])
+        st = ctx["st"]
+        X = torch.randn((k, n), dtype=torch.float64, device="cuda")
+        Y = torch.empty_like(X)
+        flush = torch.empty(64 << 20, dtype=torch.float32, device="cuda")   # 256 MB > 126 MB L2
+        res = {}
+        for flow in (0, 1):
+            P.set_option(hb.OPT_FLOW_KERNEL, flow)
+            P.set_option(hb.OPT_USE_GRAPH, 1)
+            for _ in range(3):
+                P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=st)
+            l0 = P.launch_count()
+            ts = []
+            for _ in range(steps):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=st)
+                e1.record()
+                torch.cuda.synchronize()
+                ts.append(e0.elapsed_time(e1))
+            ts.sort()
+            res[flow] = (ts[len(ts) // 2], (P.launch_count() - l0) // steps, Y.clone())
+        fl, by = P.flops(k), P.algorithmic_bytes(k)
+        ms = res[1][0]
+        t_mem, t_flop = by / (peaks["hbm"] * 1e9) * 1e3, fl / (peaks["fp64"] * 1e12) * 1e3
+        out = {"workload": what, "n": n, "leafsize": leaf, "ranks": [rmin, rmax], "nrhs": k, "value": fl / ms * 1e-6, "unit": "GFLOP/s",
+               "hbm_gbs": by / ms * 1e-6, "ms_per_step": ms, "steps": steps, "timing": "median of per-product CUDA-event times, L2 flushed between products",
+               "launches_per_product": res[1][1], "kernel": "persistent dataflow kernel (csrc/hssb_flow.cuh), CUDA-graph replay",
+               "one_launch_per_level": {"ms_per_step": res[0][0], "launches_per_product": res[0][1]},
+               "matches_level_launches_bit_for_bit": bool(torch.equal(res[0][2], res[1][2])),
+               "product_roofline": {"flops": fl, "algorithmic_bytes": by, "t_mem_ms": t_mem, "t_flop_ms": t_flop,
+                                    "binding": "tensor" if t_flop >= t_mem else "hbm", "frac_of_roofline": max(t_mem, t_flop) / ms,
+                                    "note": "latency-bound: 2*depth+2 dependent levels of ~4 us each"}}
+        P.close()
+        del flush
+        torch.cuda.empty_cache()
+        return out
+    except Exception as e:   # an extra must never take the headline line down
+        try:
+            torch.cuda.synchronize()
+        except Exception:
+            pass
+        return {"error": repr(e)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -667,6 +740,11 @@ def main():
             res = run_extra(ctx, nm, max(3, min(args.steps, 10)), 3, peaks)
             if rank == 0:
                 extra[nm] = res
+        if rank == 0 and N == 1:   # shapes of BASELINE configs 1-2 (variable-rank trees, any-shape kernels)
+            extra["c1_shape"] = run_small_tree_extra(ctx, "tree of config 1's shape: bisection of n=2001 with leafsize 64 (62/63-row leaves), per-node ranks 9-20, nrhs 16",
+                                                     2001, 64, 9, 20, 16, 20, peaks)
+            extra["c2_shape"] = run_small_tree_extra(ctx, "tree of config 2's shape: n=2^16, leafsize 64, per-node ranks 13-20, nrhs 64",
+                                                     2 ** 16, 64, 13, 20, 64, 20, peaks)
         if rank == 0:
             out["extra"] = extra
     if N > 1:

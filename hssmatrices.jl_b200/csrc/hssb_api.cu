@@ -14,6 +14,7 @@
 
 #include <algorithm>
 #include <functional>
+#include <map>
 #include <memory>
 #include <mutex>
 #include <new>
@@ -38,11 +39,12 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
   if (g_trap_host && g_trap_host[0]) {  // a kernel gave up waiting: say for what
     static const char* what[] = {"?", "a shared-memory mbarrier (TMA data or a ring slot)", "the grid barrier of the tree kernel",
-                                 "a peer's acknowledgement of the previous exchange", "a peer's subtree-root block (exchange)"};
+                                 "a peer's acknowledgement of the previous exchange", "a peer's subtree-root block (exchange)",
+                                 "the producer task of an operand (dataflow kernel)"};
     const unsigned long long c = g_trap_host[0];
     const size_t len = strlen(g_err);
     snprintf(g_err + len, sizeof(g_err) - len, " [a kernel timed out waiting for %s: wanted %llu, saw %llu, block %llu thread %llu]",
-             what[c < 5 ? c : 0], g_trap_host[1], g_trap_host[2], g_trap_host[3] & 0xffffffffull, g_trap_host[3] >> 32);
+             what[c < 6 ? c : 0], g_trap_host[1], g_trap_host[2], g_trap_host[3] & 0xffffffffull, g_trap_host[3] >> 32);
   }
 }
 
@@ -990,6 +992,7 @@ static XchgParams xchg_params(const hssb_matrix* H, const CallParams& cp) {
 
 }  // namespace hssb
 #include "hssb_tree.cuh"
+#include "hssb_flow.cuh"
 #include "hssb_hostpipe.h"
 namespace hssb {
 
@@ -1008,9 +1011,19 @@ static const std::vector<Phase>& phase_list(const hssb_matrix* H, int mode) {
   return mode == 2 ? H->phases_u : mode == 1 ? H->phases_t : H->phases;
 }
 
+static bool plan_runs_generic(const hssb_matrix* H, const CallParams& cp) {
+  for (const Phase& ph : phase_list(H, cp.trans)) {
+    if (ph.kind == PH_EXCHANGE || ph.kind == PH_XCHG_ACK || ph.ntasks == 0) continue;
+    if (ph.fast && !H->force_generic && fast_phase_supported(H, ph, cp)) return false;
+  }
+  return true;
+}
+
 static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
   const std::vector<Phase>& phases = phase_list(H, cp.trans);
   const bool prof = H->profile;
+  // any-shape plans (no fixed-shape kernel applies): the whole product as one dataflow launch (hssb_flow.cuh)
+  if (flow_usable(H, cp.trans) && plan_runs_generic(H, cp)) return launch_flow(H, cp.trans, cp, st);
   if (prof) {
     H->prof_mode = cp.trans;
     while (H->prof_events.size() < phases.size() + 1) {
@@ -1316,6 +1329,7 @@ int hssb_destroy(hssb_matrix* h) {
   invalidate_graphs(h);
   free_fast(h);
   free_tree(h);
+  free_flow(h);
   for (auto e : h->prof_events) cudaEventDestroy(e);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   for (int r = 0; r < hssb_matrix::MAX_PEERS; ++r)
@@ -1463,6 +1477,10 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
   }
   if (trans == 0 && h->tree_kernel && !h->force_generic) {  // allocates: must happen outside graph capture
     rc = ensure_tree_plan(h);
+    if (rc) return rc;
+  }
+  if (h->flow_kernel && trans <= 1 && h->n_shards == 1) {  // likewise
+    rc = ensure_flow_plan(h, trans, nrhs);
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
@@ -1745,6 +1763,8 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
       if (value < 1 || value > 3) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_LEAF_KERNEL: 1, 2 or 3");
       h->leaf_kernel = (int)value;
       break;
+    case HSSB_OPT_LEAF_FUSION: h->leaf_fusion = value != 0; break;
+    case HSSB_OPT_FLOW_KERNEL: h->flow_kernel = value != 0; break;
     case HSSB_OPT_HOST_BOUNCE:
       if (value < 0 || value > 2) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_HOST_BOUNCE: 0, 1 or 2");
       h->host_bounce = (int)value;
@@ -1783,6 +1803,12 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
     case HSSB_OPT_TREE_KERNEL: return h->tree_kernel;
     case HSSB_OPT_HOST_BOUNCE: return h->host_bounce;
     case HSSB_OPT_LEAF_KERNEL: return h->leaf_kernel;
+    case HSSB_OPT_LEAF_FUSION: return h->leaf_fusion;
+    case HSSB_OPT_FLOW_KERNEL: {
+      if (!h->flow_kernel) return 0;
+      const FlowPlan* fp = (const FlowPlan*)h->flow_plan[0];
+      return fp && fp->usable ? 2 : 1;  // 2: the product plan qualifies and has been set up
+    }
     case HSSB_OPT_LAST_BOUNCE: return h->last_bounce;
     default: return -1;
   }

@@ -53,7 +53,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded waits: a protocol bug must trap (and surface as a CUDA error), never hang the GPU.  Before the trap the
 // waiter says what it was waiting for in host-mapped memory (the context is gone afterwards, host memory is not);
 // set_error() appends it to the CUDA error text.
-enum TrapCode : unsigned long long { TRAP_MBAR = 1, TRAP_GRID = 2, TRAP_PEER_ACK = 3, TRAP_PEER_DATA = 4 };
+enum TrapCode : unsigned long long { TRAP_MBAR = 1, TRAP_GRID = 2, TRAP_PEER_ACK = 3, TRAP_PEER_DATA = 4, TRAP_FLOW = 5 };
 static __device__ unsigned long long* g_trap_slot = nullptr;
 __device__ __noinline__ void trap_report(unsigned long long code, unsigned long long a, unsigned long long b) {
   unsigned long long* s = g_trap_slot;
@@ -653,7 +653,44 @@ static int make_x_map(CUtensorMap* map, const double* X, int64_t rows, int64_t n
 
 }  // namespace hssb
 #include "hssb_leaf2.cuh"
+#include "hssb_leafx.cuh"
 namespace hssb {
+
+// ---- the "X once" variant (HSSB_OPT_LEAF_FUSION): shapes it is instantiated for
+static bool leafx_supported(int64_t m, int64_t r) { return m == 128 && (r == 32 || r == 64); }
+
+template <int M, int R>
+static int launch_leafx(hssb_matrix* H, const Phase& ph, const Phase& up, const Phase& down, const CallParams& cp, cudaStream_t st) {
+  constexpr int NT = 8192 / M, KC = 16;
+  FastState* fs = (FastState*)H->fast_state;
+  const int ntiles = (cp.nrhs + NT - 1) / NT;
+  const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
+  if (ph.kind == PH_LEAF_UP) {
+    using C = LeafXUpCfg<M, R, NT, KC>;
+    CUtensorMap xmap;
+    if (int rc = make_x_map(&xmap, cp.X, H->local_n, cp.nrhs, cp.ldx, NT)) return rc;
+    if (int rc = fs->configure((const void*)leafx_up_kernel<M, R, NT, KC>, C::SMEM)) return rc;
+    leafx_up_kernel<M, R, NT, KC><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + up.task0, H->tasks_dev + down.task0, (int)ph.ntasks, ntiles, cp, xmap);
+  } else {
+    using C = LeafXDownCfg<M, R, NT>;
+    if (int rc = fs->configure((const void*)leafx_down_kernel<M, R, NT>, C::SMEM)) return rc;
+    leafx_down_kernel<M, R, NT><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + down.task0, (int)ph.ntasks, ntiles, cp);
+  }
+  H->launches++;
+  HSSB_CUDA(cudaGetLastError());
+  return HSSB_OK;
+}
+
+// Both leaf phases of the product plan when the fused variant can run them, else nullptr.
+static bool leafx_phases(const hssb_matrix* H, const CallParams& cp, const Phase*& up, const Phase*& down) {
+  up = down = nullptr;
+  if (!H->leaf_fusion || cp.trans != 0 || !H->uniform || !H->padded || !leafx_supported(H->uni_m, H->uni_r)) return false;
+  for (const Phase& q : H->phases) {
+    if (q.kind == PH_LEAF_UP && q.fast == FAST_LEAF_UP && !q.fast_m) up = &q;
+    if (q.kind == PH_LEAF_DOWN && q.fast == FAST_LEAF_DOWN && !q.fast_m) down = &q;
+  }
+  return up && down && up->ntasks == down->ntasks;
+}
 
 template <int M, int R, bool DOWN, int NT, int KC>
 static int launch_leaf2(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
@@ -802,6 +839,11 @@ static int launch_fast(hssb_matrix* H, const Phase& ph, const CallParams& cp, cu
     }
   } else {
     const bool down = ph.fast == FAST_LEAF_DOWN;
+    const Phase *xu, *xd;
+    if (!ph.fast_m && leafx_phases(H, cp, xu, xd)) {  // opt-in: one pass over X for D X and V' X (north star (2))
+      if (m == 128 && r == 32) return launch_leafx<128, 32>(H, ph, *xu, *xd, cp, st);
+      if (m == 128 && r == 64) return launch_leafx<128, 64>(H, ph, *xu, *xd, cp, st);
+    }
 #define HSSB_LEAF_CASE(MM, RR) if (m == MM && r == RR) return launch_leaf<MM, RR>(H, ph, cp, st, down);
     HSSB_LEAF_CASE(128, 16) HSSB_LEAF_CASE(128, 32) HSSB_LEAF_CASE(128, 64)
     HSSB_LEAF_CASE(256, 16) HSSB_LEAF_CASE(256, 32) HSSB_LEAF_CASE(256, 64)

@@ -240,5 +240,11 @@ struct hssb_matrix {
   // leaf kernels: 2 = second generation (hssb_leaf2.cuh, default), 1 = first generation (hssb_fast.cuh, cross-check),
   // 3 = second generation with longer chunks where instantiated (measurement)
   int leaf_kernel = 2;
+  // HSSB_OPT_LEAF_FUSION: 1 = the "X once" variant (hssb_leafx.cuh): leaf-up forms D X and V' X in one pass over X and
+  // parks alpha D X + beta Y in Y, leaf-down adds alpha U F.  Measured slower than the two-pass default.
+  int leaf_fusion = 0;
+  // HSSB_OPT_FLOW_KERNEL: any-shape plans of single-shard handles run as ONE persistent dataflow kernel (hssb_flow.cuh)
+  int flow_kernel = 1;
+  void* flow_plan[2] = {nullptr, nullptr};  // [0] Y = A X, [1] Y = A' X on the any-shape task table
   void* tree_plan = nullptr;
 };

@@ -34,17 +34,12 @@ __device__ __forceinline__ const double* operand_b(const CallParams& p, int src,
 constexpr int G_SA = 68, G_SB = 20, G_SMEM = G_TM * G_SB;  // 1280 >= 16 * 68
 static_assert(G_TK * G_SA <= G_SMEM, "k-major image must fit");
 
-__global__ void __launch_bounds__(G_THREADS, 3)
-generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
-  const GTask t = tasks[blockIdx.x];
-  const int m0 = blockIdx.y * G_TM;
-  if (m0 >= t.M) return;
-  const int n0 = blockIdx.z * G_TN;
+// One 64 x 64 output tile (rows m0.., right-hand sides n0..) of one task.  WS_CG: operands from the Z / F
+// workspaces are read with ld.global.cg (L2 only) -- needed when the producer of the block ran in the SAME launch
+// on another SM (hssb_flow.cuh), where a stale L1 line would be a wrong answer.
+template <bool WS_CG>
+__device__ __forceinline__ void generic_tile(const GTask& t, const int m0, const int n0, const CallParams& p, double* As, double* Bs) {
   const int N = p.nrhs;
-
-  __shared__ double As[G_SMEM];
-  __shared__ double Bs[G_SMEM];
-
   const int tid = threadIdx.x;
   // FP64 tensor path: 8 warps tile the 64 x 64 output as 2 (M) x 4 (N); a warp owns 32 x 16 =
   // 4 x 2 m8n8 accumulators (DMMA m8n8k4), lane = 4 g + q.
@@ -78,6 +73,7 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
     const bool ta = s1 ? t.ta1 : t.ta0;
     const double* B = s1 ? B1 : B0;
     const int64_t ldb = s1 ? ldb1 : ldb0;
+    const bool ws = WS_CG && (s1 ? t.sb1 : t.sb0) != SRC_X;
     if (!ta) {
       const int mm = tid & 63;
 #pragma unroll
@@ -97,7 +93,9 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
       const int nn = (tid >> 4) + 16 * r;
-      rb[r] = (n0 + nn < N && k0 + kk < K) ? B[(int64_t)(n0 + nn) * ldb + (k0 + kk)] : 0.0;
+      const bool in = n0 + nn < N && k0 + kk < K;
+      const double* src = B + (int64_t)(n0 + nn) * ldb + (k0 + kk);
+      rb[r] = in ? (ws ? __ldcg(src) : *src) : 0.0;
     }
   };
   auto stage = [&](int slab) {  // registers -> shared memory, same element mapping as fetch()
@@ -166,6 +164,16 @@ generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
         *dst = v;
       }
     }
+}
+
+__global__ void __launch_bounds__(G_THREADS, 3)
+generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
+  __shared__ double As[G_SMEM];
+  __shared__ double Bs[G_SMEM];
+  const GTask t = tasks[blockIdx.x];
+  const int m0 = blockIdx.y * G_TM;
+  if (m0 >= t.M) return;
+  generic_tile<false>(t, m0, blockIdx.z * G_TN, p, As, Bs);
 }
 
 }  // namespace hssb

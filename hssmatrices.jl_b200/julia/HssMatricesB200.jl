@@ -103,6 +103,59 @@ function pack(hssA::HssMatrix{Float64}; device::Integer=0)
   return PackedHss(href[], size(hssA, 1), size(hssA, 2))
 end
 
+"""
+    pack(hssA, devices::AbstractVector{<:Integer}) -> PackedGroup
+
+One process, one `ccall`, several GPUs (SURVEY §8b): the tree is registered ONCE and sharded by subtree over
+`devices` (a power of two of them) inside the library (`hssb_group_finalize`); `*` / `mul!` on the result take the
+whole X and Y and drive every device from the calling Julia thread.  No MPI.jl, no Distributed.jl.
+"""
+mutable struct PackedGroup
+  handle::Ptr{Cvoid}
+  m::Int
+  n::Int
+  function PackedGroup(handle, m, n)
+    g = new(handle, m, n)
+    finalizer(g) do q
+      q.handle == C_NULL || ccall((:hssb_group_destroy, libhssb), Cint, (Ptr{Cvoid},), q.handle)
+      q.handle = C_NULL
+    end
+    return g
+  end
+end
+Base.size(g::PackedGroup) = (g.m, g.n)
+Base.size(g::PackedGroup, d::Integer) = size(g)[d]
+
+function pack(hssA::HssMatrix{Float64}, devices::AbstractVector{<:Integer})
+  bref = Ref{Ptr{Cvoid}}(C_NULL)
+  check(ccall((:hssb_builder_create, libhssb), Cint, (Ref{Ptr{Cvoid}},), bref))
+  gref = Ref{Ptr{Cvoid}}(C_NULL)
+  devs = Cint.(collect(devices))
+  try
+    root = addnode(bref[], hssA, true)
+    check(ccall((:hssb_group_finalize, libhssb), Cint, (Ptr{Cvoid}, Int64, Ptr{Cint}, Cint, Ref{Ptr{Cvoid}}),
+                bref[], root, devs, length(devs), gref))
+  finally
+    ccall((:hssb_builder_destroy, libhssb), Cvoid, (Ptr{Cvoid},), bref[])
+  end
+  return PackedGroup(gref[], size(hssA, 1), size(hssA, 2))
+end
+
+function mul!(C::StridedMatrix{Float64}, g::PackedGroup, B::StridedMatrix{Float64}, α::Real, β::Real)
+  size(g, 2) == size(B, 1) || throw(DimensionMismatch("First dimension of B does not match second dimension of A. Expected $(size(g, 2)), got $(size(B, 1))"))
+  size(C) == (size(g, 1), size(B, 2)) || throw(DimensionMismatch("Dimensions of C don't match up with A and B."))
+  (stride(B, 1) == 1 && stride(C, 1) == 1) || throw(ArgumentError("B and C need unit stride in the first dimension"))
+  GC.@preserve B C begin
+    check(ccall((:hssb_group_matmul, libhssb), Cint,
+      (Ptr{Cvoid}, Int64, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64, Float64, Float64),
+      g.handle, size(C, 1), size(B, 1), size(B, 2), pointer(B), max(stride(B, 2), 1), pointer(C), max(stride(C, 2), 1),
+      Float64(α), Float64(β)))
+  end
+  return C
+end
+*(g::PackedGroup, B::StridedMatrix{Float64}) = mul!(Matrix{Float64}(undef, size(g, 1), size(B, 2)), g, B, 1.0, 0.0)   # src/matmul.jl:13
+*(g::PackedGroup, x::StridedVector{Float64}) = reshape(g * reshape(x, length(x), 1), length(x))                      # src/matmul.jl:15
+
 # mul!(C, hssA, B, α, β): src/matmul.jl:18-28.  β == 0 never reads C (src/matmul.jl:13 passes
 # uninitialised memory).
 function mul!(C::StridedMatrix{Float64}, p::PackedHss, B::StridedMatrix{Float64}, α::Real, β::Real)
@@ -211,6 +264,6 @@ mul!(C::StridedMatrix{Float64}, hssA::HssMatrix{Float64}, B::StridedMatrix{Float
 *(hssA::HssMatrix{Float64}, B::StridedMatrix{Float64}) = packed(hssA) * B
 *(A::StridedMatrix{Float64}, hssB::HssMatrix{Float64}) = A * packed(hssB)
 
-export pack, PackedHss, invalidate!, ulvfactor!
+export pack, PackedHss, PackedGroup, invalidate!, ulvfactor!
 
 end # module

@@ -230,6 +230,17 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
                                     together with the matching rows of X (csrc/hssb_leaf2.cuh); 1 = first generation (whole X block
                                     resident and double buffered, csrc/hssb_fast.cuh), kept as a bit-identical cross-check; 3 = second
                                     generation with longer chunks (measurement)                                                     */
+#define HSSB_OPT_LEAF_FUSION 13  /* 0 (default): two passes over X (leaf-up V' X, leaf-down D X + U F).  1: the "X once" variant of
+                                    csrc/hssb_leafx.cuh -- leaf-up reads each X block once for BOTH D X and V' X ([D ; V'] streamed as one
+                                    stacked operand) and parks alpha D X + beta Y in Y, leaf-down adds alpha U F.  Uniform trees with
+                                    (leaf, rank) in {(128,32), (128,64)}; other shapes keep the default.  Same results to
+                                    rounding; measured slower (Y is written twice and read once more), kept as the measured alternative */
+#define HSSB_OPT_FLOW_KERNEL 14  /* 1 (default): trees no fixed-shape kernel applies to (ragged leaves, variable ranks: every matrix that
+                                    comes out of a compression) run the WHOLE product as one persistent dataflow kernel: tasks are drawn
+                                    from a queue in level order and wait on per-task counters for the producers of their operands, so
+                                    the 2*depth+2 dependent levels cost a flag round trip each instead of a launch (csrc/hssb_flow.cuh).
+                                    Single-shard handles, product and transposed product.  0: one launch per level.  hssb_get_option
+                                    returns 2 once the product plan has been set up for it                                          */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */

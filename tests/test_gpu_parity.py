@@ -395,3 +395,72 @@ def test_pageable_large_call_is_staged(gpu, oracle):
         P.mul_(Yh.numpy().T, Xh.numpy().T)
         assert P.get_option(gpu.OPT_LAST_BOUNCE) == 0
         assert np.array_equal(Yh.numpy().T, Yp)
+
+
+@pytest.mark.parametrize("r", [32, 64])
+def test_leaf_fusion_x_once_variant(gpu, oracle, r):
+    """BASELINE north star (2): the fused leaf kernel that reads each X block ONCE for D X and V' X
+    (HSSB_OPT_LEAF_FUSION = 1, csrc/hssb_leafx.cuh) against the two-pass default and the oracle, incl. alpha / beta
+    (the fused leaf-up parks alpha D X + beta Y in Y, the leaf-down adds alpha U F)."""
+    n, ls, seed = 8192, 128, 90 + r
+    h = oracle.synthetic_hss(n, ls, r, seed)
+    rng = np.random.default_rng(r)
+    with gpu.synthetic(n, ls, r, seed) as P:
+        for k in (1, 20, 64, 130):
+            X = oracle.synth_x(seed + k, n, k)
+            ref = oracle.matmul(h, X)
+            P.set_option(gpu.OPT_LEAF_FUSION, 0)
+            l0 = P.launch_count()
+            Y0 = P @ X
+            n0 = P.launch_count() - l0
+            P.set_option(gpu.OPT_LEAF_FUSION, 1)
+            assert P.get_option(gpu.OPT_LEAF_FUSION) == 1
+            l0 = P.launch_count()
+            Y1 = P @ X
+            assert P.launch_count() - l0 == n0            # same number of launches: both leaf kernels are replaced
+            assert relerr(Y1, ref) <= TOL and relerr(Y1, Y0) <= 1e-14, (r, k)
+            C0 = rng.standard_normal((n, k))
+            got = P.mul_(np.asfortranarray(C0.copy()), X, 0.7, -1.3)
+            assert relerr(got, oracle.mul(C0.copy(), h, X, 0.7, -1.3)) <= TOL
+            got = P.mul_(np.full((n, k), np.nan, order="F"), X, 2.0, 0.0)   # beta == 0 never reads C
+            assert np.isfinite(got).all() and relerr(got, 2.0 * ref) <= TOL
+        assert relerr(P.tmatmul(X), oracle.matmul(oracle.adjoint(h), X)) <= TOL  # over the adjoint twin pool as well
+
+
+@pytest.mark.parametrize("n,leafsize,nrhs,rmin,rmax", [(2001, 64, 16, 9, 20), (777, 50, 5, 1, 9), (4000, 128, 130, 5, 40), (300, 40, 3, 0, 2)])
+def test_dataflow_kernel_any_shape_trees(gpu, oracle, n, leafsize, nrhs, rmin, rmax):
+    """Trees no fixed-shape kernel applies to run the whole product as ONE persistent dataflow launch
+    (HSSB_OPT_FLOW_KERNEL, csrc/hssb_flow.cuh): same tiles, same arithmetic as one launch per level -> identical
+    results, one kernel per product; also for A' X on the any-shape transposed task table, with alpha / beta, and
+    on repeated calls (the counters are reset by every launch)."""
+    rng = np.random.default_rng(n + nrhs)
+    rcl = oracle.bisection_cluster(n, leafsize)
+    h = oracle.random_hss(rcl, rcl, rng, rmin, rmax)
+    X = rng.standard_normal((n, nrhs))
+    ref = oracle.matmul(h, X)
+    tree = to_product_tree(gpu, h)
+    P = tree.repack()
+    P.set_option(gpu.OPT_PIPELINE_COLS, 1 << 20)      # one column block per host call: launches are countable
+    P.set_option(gpu.OPT_FLOW_KERNEL, 0)
+    l0 = P.launch_count()
+    Y0 = P @ X
+    per_level = P.launch_count() - l0
+    T0 = P.tmatmul(X)
+    P.set_option(gpu.OPT_FLOW_KERNEL, 1)
+    for _ in range(3):
+        l0 = P.launch_count()
+        Y1 = P @ X
+        assert P.launch_count() - l0 == 1 and per_level > 1
+        assert np.array_equal(Y1, Y0)
+    assert P.get_option(gpu.OPT_FLOW_KERNEL) == 2
+    assert relerr(Y1, ref) <= TOL
+    l0 = P.launch_count()
+    T1 = P.tmatmul(X)
+    assert P.launch_count() - l0 == 1
+    assert np.array_equal(T1, T0) and relerr(T1, oracle.matmul(oracle.adjoint(h), X)) <= TOL
+    C0 = rng.standard_normal((n, nrhs))
+    got = P.mul_(np.asfortranarray(C0.copy()), X, 0.7, -1.3)
+    assert relerr(got, oracle.mul(C0.copy(), h, X, 0.7, -1.3)) <= TOL
+    X2 = rng.standard_normal((n, 2 * nrhs + 1))       # more column tiles than before: the counters grow
+    assert relerr(P @ X2, oracle.matmul(h, X2)) <= TOL
+    P.close()

@@ -1,0 +1,34 @@
+"""Any-shape trees: one launch per level (graph replay) against the dataflow kernel (HSSB_OPT_FLOW_KERNEL)."""
+import os, sys, time
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path[:0] = [ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")]
+import numpy as np
+import torch
+import hssb200 as hb
+import hss_oracle as o
+from test_plan_cpu import to_product_tree
+s = torch.cuda.Stream(); torch.cuda.set_stream(s)
+for name, n, leaf, rmin, rmax, k in (("c1-like n=2001 leaf 64 ranks 9-20", 2001, 64, 9, 20, 16), ("c2-like n=2^16 leaf 64 ranks 13-20", 2 ** 16, 64, 13, 20, 64)):
+    rng = np.random.default_rng(5)
+    cl = o.bisection_cluster(n, leaf)
+    h = o.random_hss(cl, cl, rng, rmin, rmax)
+    P = hb.pack(to_product_tree(hb, h))
+    P.set_option(hb.OPT_USE_GRAPH, 1)
+    X = torch.randn((k, n), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
+    fl, by = P.flops(k), P.algorithmic_bytes(k)
+    out = []
+    for flow in (0, 1, 0, 1):
+        P.set_option(hb.OPT_FLOW_KERNEL, flow)
+        for _ in range(3):
+            P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=s.cuda_stream)
+        l0 = P.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(50):
+            P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=s.cuda_stream)
+        e1.record(); torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / 50
+        out.append((flow, (P.launch_count() - l0) // 50, round(ms * 1e3, 1)))
+    t_flop, t_mem = fl / 37.1e12, by / 6.4686e12
+    print(f"{name}: flops {fl:.3e} bytes {by:.3e} roofline {max(t_flop, t_mem) * 1e6:.1f} us | (flow, launches, us):", out)
+    P.close()
