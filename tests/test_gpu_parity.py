@@ -328,6 +328,48 @@ def test_full_size_config3_properties(gpu, oracle):
         assert (torch.linalg.norm(Y2 - Y1) / torch.linalg.norm(Y1)).item() <= TOL
 
 
+@pytest.mark.parametrize("name,n,ls,r,k", [("config 4", 2 ** 22, 128, 64, 128), ("config 5", 2 ** 24, 256, 64, 32)])
+def test_full_size_configs_4_and_5(gpu, oracle, name, n, ls, r, k):
+    """BASELINE configs 4 and 5 at FULL size on one GPU (15 GB / 64 GB of generators, generated on the device):
+    sparse-support right-hand side checked leaf by leaf against the lazily evaluated oracle (leaves next to the
+    support, in the other half of the tree and at both ends), and linearity on dense inputs."""
+    import torch
+    seed = 3
+    free, _ = torch.cuda.mem_get_info()
+    need = 8 * (n // ls) * (ls * ls + 2 * ls * r) * 1.1 + 5 * 8 * n * k
+    if free < need:
+        pytest.skip(f"{name} needs {need / 1e9:.0f} GB of device memory, {free / 1e9:.0f} GB free")
+    with gpu.synthetic(n, ls, r, seed) as P:
+        L = n // ls
+        assert P.info.uniform == 1 and P.info.n_leaves == L
+        assert (P.algorithmic_bytes(k), P.flops(k)) == oracle.synthetic_counts(n, ls, r, k)
+        st = torch.cuda.current_stream().cuda_stream
+        s_lo, s_len = 5 * ls + 17, 3 * ls
+        Xs = np.random.default_rng(0).standard_normal((s_len, k))
+        X = torch.zeros((k, n), dtype=torch.float64, device="cuda")
+        X[:, s_lo:s_lo + s_len] = torch.from_numpy(np.ascontiguousarray(Xs.T)).cuda()
+        Y = torch.empty((k, n), dtype=torch.float64, device="cuda")
+        P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=st)
+        torch.cuda.synchronize()
+        targets = [0, 5 * ls, 6 * ls, 7 * ls, 8 * ls, (L // 2) * ls, (L - 1) * ls, (5 * L // 8 + 3) * ls]
+        lazy = oracle.LazySyntheticHss(n, ls, r, seed).rows(targets, s_lo, Xs)
+        for lo, yref in lazy.items():
+            got = Y[:, lo:lo + ls].cpu().numpy().T
+            assert relerr(got, yref) <= TOL, (name, lo)
+        g = torch.Generator(device="cuda").manual_seed(1)
+        X1 = torch.randn((k, n), dtype=torch.float64, device="cuda", generator=g)
+        X2 = torch.randn((k, n), dtype=torch.float64, device="cuda", generator=g)
+        Y1, Y2 = (torch.empty((k, n), dtype=torch.float64, device="cuda") for _ in range(2))
+        P.matmul_dev(X1.data_ptr(), n, Y1.data_ptr(), n, k, stream=st)
+        P.matmul_dev(X2.data_ptr(), n, Y2.data_ptr(), n, k, stream=st)
+        X1.mul_(0.5).add_(X2, alpha=-2.0)
+        P.matmul_dev(X1.data_ptr(), n, Y.data_ptr(), n, k, stream=st)
+        torch.cuda.synchronize()
+        Y1.mul_(0.5).add_(Y2, alpha=-2.0)
+        assert (torch.linalg.norm(Y - Y1) / torch.linalg.norm(Y1)).item() <= TOL
+    torch.cuda.empty_cache()
+
+
 def test_two_gpu_sharded(gpu, oracle):
     """Subtree sharding over NCCL (skipped on a 1-GPU box; the plan itself is
     covered on CPU by tests/test_plan_cpu.py::test_sharded_plan)."""
