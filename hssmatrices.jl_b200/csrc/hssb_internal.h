@@ -232,6 +232,9 @@ struct hssb_matrix {
     int64_t kernels = 0;
   };
   std::vector<GraphSlot> graphs;
+  int graph_miss_streak = 0;            // consecutive calls whose signature was not in the cache
+  hssb::CallParams graph_plain_cp;      // last signature that was launched plainly instead of captured
+  bool graph_plain_valid = false;
   // fixed-shape kernel state (hssb_fast.cuh)
   void* fast_state = nullptr;
   // persistent tree kernel (hssb_tree.cuh): 1 = all merge / translate levels (and the peer exchange) in one

@@ -506,3 +506,31 @@ def test_dataflow_kernel_any_shape_trees(gpu, oracle, n, leafsize, nrhs, rmin, r
     X2 = rng.standard_normal((n, 2 * nrhs + 1))       # more column tiles than before: the counters grow
     assert relerr(P @ X2, oracle.matmul(h, X2)) <= TOL
     P.close()
+
+
+def test_graph_cache_with_fresh_pointers(gpu, oracle):
+    """HSSB_OPT_USE_GRAPH with caller-owned device arrays: a repeating pointer set is captured once and replayed;
+    fresh arrays on every call fall back to plain launches after two misses (no capture + instantiate per call), and a
+    set that then repeats is captured again.  Same results either way."""
+    import torch
+    n, ls, r, k, seed = 8192, 128, 32, 64, 11
+    h = oracle.synthetic_hss(n, ls, r, seed)
+    X0 = oracle.synth_x(seed, n, k)
+    ref = oracle.matmul(h, X0)
+    st = torch.cuda.current_stream().cuda_stream
+    with gpu.synthetic(n, ls, r, seed) as P:
+        P.set_option(gpu.OPT_USE_GRAPH, 1)
+        keep = []
+        for i in range(8):                      # fresh X / Y every call
+            X = torch.from_numpy(np.ascontiguousarray(X0.T)).cuda()
+            Y = torch.full((k, n), float("nan"), dtype=torch.float64, device="cuda")
+            keep.append((X, Y))
+            P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=st)
+            torch.cuda.synchronize()
+            assert relerr(Y.cpu().numpy().T, ref) <= TOL, i
+        X, Y = keep[0]
+        for i in range(4):                      # now a stable pair: captured on its second appearance, then replayed
+            Y.fill_(float("nan"))
+            P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=st)
+            torch.cuda.synchronize()
+            assert relerr(Y.cpu().numpy().T, ref) <= TOL, i
