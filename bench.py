@@ -592,6 +592,29 @@ def main():
         Xh = torch.empty((k, rows), dtype=torch.float64).pin_memory()
         Yh = torch.empty((k, rows), dtype=torch.float64).pin_memory()
         Xh.copy_(X)
+        # what the box's PCIe / host-memory fabric gives THIS rank while every rank of the job copies both ways at
+        # once (plain cudaMemcpyAsync of the same pinned buffers, no kernels): the floor of the end-to-end leg
+        s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+        dtmp = torch.empty_like(X)
+
+        def duplex():
+            with torch.cuda.stream(s_in):
+                dtmp.copy_(Xh, non_blocking=True)
+            with torch.cuda.stream(s_out):
+                Yh.copy_(Y, non_blocking=True)
+        duplex()
+        torch.cuda.synchronize()
+        barrier(ctx)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            duplex()
+        torch.cuda.synchronize()
+        barrier(ctx)
+        tc = torch.tensor([(time.perf_counter() - t0) / 3], dtype=torch.float64, device="cuda")
+        if N > 1:
+            dist.all_reduce(tc, op=dist.ReduceOp.MAX)
+        t_copy = tc.item()
+        del dtmp
         xs, ys = Xh.numpy().T, Yh.numpy().T  # column-major (rows x k) views of the pinned buffers
         t_pin = e2e_leg(xs, ys, steps_e)
         chk = float(torch.linalg.norm(torch.from_numpy(ys[:, 0]) - Y[0].cpu()) / torch.linalg.norm(Y[0].cpu()))
@@ -604,11 +627,14 @@ def main():
         e2e = {"value": flops_all / t_pin * 1e-9, "unit": "GFLOP/s", "h2d_bytes_per_step": 8 * rows * k,
                "d2h_bytes_per_step": 8 * rows * k, "ms_per_step": t_pin * 1e3, "steps": steps_e,
                "host_memory": "pinned", "matches_device_path": chk <= 1e-12,
+               "copy_floor": {"ms_per_step": t_copy * 1e3, "gbs_per_direction_per_gpu": 8 * rows * k / t_copy * 1e-9,
+                              "what": "the same H2D and D2H bytes as plain concurrent cudaMemcpyAsync from / to the pinned buffers, all "
+                                      "ranks at once, no kernels: what the box's PCIe / host-memory fabric allows at this N"},
                "pageable": {"value": flops_all / t_page * 1e-9, "unit": "GFLOP/s", "ms_per_step": t_page * 1e3,
                             "host_memory": "pageable (numpy arrays, as a Julia Matrix would be)",
                             "staging": ("library ring of pinned 2 MiB slots + worker threads (csrc/hssb_hostpipe.h)"
                                         if staged == 3 else f"driver (cudaMemcpy2DAsync on the caller's pointer), ring bits {staged}"),
-                            "host_threads_per_direction": int(os.environ.get("HSSB_HOST_THREADS", min(8, max(2, (os.cpu_count() or 8) // 2)))),
+                            "host_threads_per_direction": int(P.get_option(hb.OPT_HOST_THREADS)),
                             "vs_pinned": t_page / t_pin, "matches_pinned": chk_p <= 1e-12}}
         del Xh, Yh, xp, yp
 

@@ -1058,6 +1058,7 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
       return fp && fp->usable ? 2 : 1;  // 2: the product plan qualifies and has been set up
     }
     case HSSB_OPT_LAST_BOUNCE: return h->last_bounce;
+    case HSSB_OPT_HOST_THREADS: return host_pool(0).size();
     default: return -1;
   }
   });

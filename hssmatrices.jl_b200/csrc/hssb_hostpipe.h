@@ -26,6 +26,9 @@
 #if defined(__x86_64__)
 #include <emmintrin.h>
 #endif
+#if defined(__linux__)
+#include <sched.h>
+#endif
 
 #include "hssb_internal.h"
 
@@ -72,8 +75,17 @@ static int host_threads_per_pool() {
     const int v = atoi(e);
     if (v >= 1 && v <= 64) return v;
   }
-  const unsigned hc = std::thread::hardware_concurrency();
-  int n = hc ? (int)hc / 2 : 4;
+  // Two pools (in / out) per process, and on a multi-GPU box one process per GPU is the usual arrangement:
+  // share the cores the process may run on between the GPUs of the box (8 GPUs on 32 cores: 2 threads per
+  // direction and process; one GPU on 16 cores: 8).
+  int cores = (int)std::thread::hardware_concurrency();
+#if defined(__linux__)
+  cpu_set_t set;
+  if (sched_getaffinity(0, sizeof(set), &set) == 0 && CPU_COUNT(&set) > 0) cores = CPU_COUNT(&set);
+#endif
+  int gpus = 1;
+  if (cudaGetDeviceCount(&gpus) != cudaSuccess || gpus < 1) { cudaGetLastError(); gpus = 1; }
+  const int n = cores > 0 ? cores / (2 * gpus) : 4;
   return n < 2 ? 2 : (n > 8 ? 8 : n);
 }
 static HostPool& host_pool(int dir) {

@@ -226,6 +226,8 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
                                     default min(8, cores / 2)), so that staging overlaps the DMA and the kernels; 0 = hand every
                                     pointer to cudaMemcpy2DAsync as it is; 2 = always stage (tests)                                 */
 #define HSSB_OPT_LAST_BOUNCE 11  /* read-only: what the last host call staged through the rings (bit 0: X, bit 1: Y)                */
+#define HSSB_OPT_HOST_THREADS 15 /* read-only: worker threads per direction of the pageable staging (HSSB_HOST_THREADS, else the cores the
+                                    process may use / (2 x GPUs of the box), clamped to 2..8)                                        */
 #define HSSB_OPT_LEAF_KERNEL 12  /* fixed-shape leaf kernels: 2 (default) = second generation, every ring stage holds a chunk of [D U] / V'
                                     together with the matching rows of X (csrc/hssb_leaf2.cuh); 1 = first generation (whole X block
                                     resident and double buffered, csrc/hssb_fast.cuh), kept as a bit-identical cross-check; 3 = second
