@@ -126,6 +126,8 @@ SIGNATURES = {
     "hssb_ulv_factor": (C.c_int, [_P]),
     "hssb_solve": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64]),
     "hssb_solve_dev": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64, _P]),
+    "hssb_solve_t": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64]),
+    "hssb_solve_t_dev": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64, _P]),
     "hssb_ulv_info": (C.c_int, [_P, _P]),
     "hssb_debug_ulv_factor_host": (C.c_int, [_P]),
     "hssb_debug_ulv_pool": (C.c_int, [_P, _P, _i64]),
@@ -741,6 +743,21 @@ class PackedHss:
         return Z
 
     ulvfactsolve = solve
+
+    def solve_t(self, B):
+        """`A' \\ B` on the same packed matrix (uniform trees: second factor pool from the adjoint twin pool)."""
+        B = _f64(B)
+        if B.ndim == 1:
+            return self.solve_t(B.reshape(-1, 1)).reshape(-1)
+        Bf = _fcol(B)
+        Z = np.empty((self.info.m, B.shape[1]), order="F")
+        _check(lib().hssb_solve_t(self._h, Bf.shape[0], Bf.shape[1], _ptr(Bf), max(Bf.shape[0], 1), _ptr(Z), max(Z.shape[0], 1)))
+        return Z
+
+    def __rtruediv__(self, A):
+        """`/(A, hssB)` (src/hssmatrix.jl:236): A / hssB = (hssB' \\ A')'."""
+        A = _f64(A)
+        return self.solve_t(np.asfortranarray(A.T)).T
 
     def solve_dev(self, b_ptr, ldb, z_ptr, ldz, nrhs, stream=None):
         """Asynchronous solve on raw device pointers."""

@@ -589,6 +589,7 @@ int hssb_destroy(hssb_matrix* h) {
   cudaFree(h->pool_dev);
   cudaFree(h->pool_t_dev);
   cudaFree(h->ulv_pool_dev);
+  cudaFree(h->ulv_pool_t_dev);
   cudaFree(h->tasks_dev);
   cudaFree(h->z_dev);
   cudaFree(h->f_dev);
@@ -692,10 +693,25 @@ static int prepare_solve(hssb_matrix* h) {
   return HSSB_OK;
 }
 
+// Mode 3 (hssb_solve_t: A' Z = B, i.e. `/(A, hssB)` of hssmatrix.jl:236 without building hssB'): on a uniform tree A'
+// has the shapes of A, so the solve plan is shared and only the factors differ -- they are computed from the adjoint
+// twin pool into a second factor pool.
+static int prepare_solve_t(hssb_matrix* h) {
+  if (h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve_t: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
+  if (h->device < 0) HSSB_FAIL(HSSB_ERR_CUDA, "plan-only handle: hssb200 has no CPU fallback, the solve needs a B200");
+  const int tw = ensure_twin(h);
+  if (tw < 0) return tw;
+  if (tw != 0)
+    HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve_t needs the adjoint twin pool (uniform tree, HSSB_OPT_ADJOINT_TWIN = 1 and room for a second "
+                              "pool on the device); for other trees pack the adjoint matrix and use hssb_solve");
+  if (!h->ulv_t_factored || !h->ulv_pool_t_dev) return ulv_factor_device(h, true);
+  return HSSB_OK;
+}
+
 static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* dX, int64_t ldx,
                            double* dY, int64_t ldy, double alpha, double beta, void* stream) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
-  if (trans == 2 && h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
+  if (trans >= 2 && h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
   // DimensionMismatch checks of matmul.jl:19-20 (for A' the roles of the two dimensions swap)
   const int64_t need_x = trans ? h->local_m : h->local_n, need_y = trans ? h->local_n : h->local_m;
   if (rows_x != need_x)
@@ -711,7 +727,7 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
   if ((rows_x > 0 && !dX) || !dY) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL matrix pointer");
   DeviceGuard dg(h->device);
   if (!dg.ok) HSSB_FAIL(HSSB_ERR_CUDA, "cudaSetDevice(%d) failed", h->device);
-  int rc = ensure_workspace(h, nrhs, trans == 2);
+  int rc = ensure_workspace(h, nrhs, trans >= 2);
   if (rc) return rc;
   const double* pool = h->pool_dev;
   if (trans == 1) {
@@ -722,6 +738,11 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
     rc = prepare_solve(h);
     if (rc) return rc;
     pool = h->ulv_pool_dev;
+  } else if (trans == 3) {
+    rc = prepare_solve_t(h);
+    if (rc) return rc;
+    pool = h->ulv_pool_t_dev;
+    trans = 2;  // same plan, other factors
   }
   if (trans == 0 && h->tree_kernel && !h->force_generic) {  // allocates: must happen outside graph capture
     rc = ensure_tree_plan(h);
@@ -782,7 +803,7 @@ static int ensure_bounce(hssb_matrix* h) {
 static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t rows_x, int64_t nrhs, const double* X, int64_t ldx,
                             double* Y, int64_t ldy, double alpha, double beta, bool prepare = false) {
   if (!h) HSSB_FAIL(HSSB_ERR_ARG, "hssb_matmul: NULL handle");
-  if (trans == 2 && h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
+  if (trans >= 2 && h->ulv.empty()) HSSB_FAIL(HSSB_ERR_STATE, "hssb_solve: %s", h->ulv_why.empty() ? "no ULV plan" : h->ulv_why.c_str());
   const int64_t need_x = trans ? h->local_m : h->local_n, need_y = trans ? h->local_n : h->local_m;
   if (rows_x != need_x)
     HSSB_FAIL(HSSB_ERR_DIM, "DimensionMismatch: first dimension of B (%lld) does not match second dimension of A (%lld)",
@@ -802,6 +823,9 @@ static int matmul_host_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t r
     if (a < 0) return a;
   } else if (trans == 2) {
     const int a = prepare_solve(h);
+    if (a) return a;
+  } else if (trans == 3) {
+    const int a = prepare_solve_t(h);
     if (a) return a;
   }
   if (int rc = ensure_host_entry(h, nrhs)) return rc;
@@ -946,6 +970,16 @@ int hssb_solve_dev(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* dB,
   return matmul_dev_impl(h, 2, rows, rows, nrhs, dB, ldb, dZ, ldz, 1.0, 0.0, stream);
 }
 
+// A' \ B: `/(A, hssB) = ulvfactsolve(hssB', collect(A'))'` (hssmatrix.jl:236) without the adjoint copy
+int hssb_solve_t(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* B, int64_t ldb, double* Z, int64_t ldz) {
+  return matmul_host_impl(h, 3, rows, rows, nrhs, B, ldb, Z, ldz, 1.0, 0.0);
+}
+
+int hssb_solve_t_dev(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* dB, int64_t ldb, double* dZ, int64_t ldz,
+                     void* stream) {
+  return matmul_dev_impl(h, 3, rows, rows, nrhs, dB, ldb, dZ, ldz, 1.0, 0.0, stream);
+}
+
 int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* o) {
   return guarded<int>([&]() -> int {
   if (!h || !o) HSSB_FAIL(HSSB_ERR_ARG, "hssb_ulv_info: NULL argument");
@@ -979,10 +1013,11 @@ static int rebuild_ulv_plan(hssb_matrix* h) {
     if (h->stream) cudaStreamSynchronize(h->stream);
     invalidate_graphs(h);
     cudaFree(h->ulv_pool_dev);
-    h->ulv_pool_dev = nullptr;
+    cudaFree(h->ulv_pool_t_dev);
+    h->ulv_pool_dev = h->ulv_pool_t_dev = nullptr;
   }
   h->ulv_pool_host.clear();
-  h->ulv_factored = false;
+  h->ulv_factored = h->ulv_t_factored = false;
   h->ws_ulv = false;  // the solve's workspace rows change with the form: re-sized by the next solve
   h->tasks_host.resize((size_t)h->ulv_task0);
   build_plan_ulv(h);

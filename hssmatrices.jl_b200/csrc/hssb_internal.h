@@ -158,6 +158,8 @@ struct hssb_matrix {
   int64_t ulv_flops_per_rhs = 0;
   int32_t ulv_MI = 0, ulv_NI = 0, ulv_KR = 0, ulv_KW = 0;  // scratch maxima
   double* ulv_pool_dev = nullptr;
+  double* ulv_pool_t_dev = nullptr;   // factors of A' (from the adjoint twin pool): hssb_solve_t
+  bool ulv_t_factored = false;
   std::vector<double> ulv_pool_host;  // plan-only handles: factorised on the host by the test hook
   bool ulv_factored = false;
   bool ulv_fast_form = true;          // HSSB_OPT_ULV_FAST (default on since it ran green on hardware: solve 2.60 -> 1.79 ms on config 3)

@@ -336,13 +336,19 @@ static int ulv_factor_host(hssb_matrix* H) {
 }
 
 // Device factorisation: one launch per tree level, one CTA per node.
-static int ulv_factor_device(hssb_matrix* H) {
-  if (H->ulv_pool_dev) { cudaFree(H->ulv_pool_dev); H->ulv_pool_dev = nullptr; }
-  H->ulv_factored = false;
+// adjoint = true factorises A' from the adjoint twin pool (uniform trees: same shapes, hence the same solve plan)
+// into a second factor pool: hssb_solve_t, i.e. `/(A, hssB)` (hssmatrix.jl:236).
+static int ulv_factor_device(hssb_matrix* H, bool adjoint = false) {
+  double*& fpool_dev = adjoint ? H->ulv_pool_t_dev : H->ulv_pool_dev;
+  bool& factored = adjoint ? H->ulv_t_factored : H->ulv_factored;
+  const double* gen_pool = adjoint ? H->pool_t_dev : H->pool_dev;
+  if (!gen_pool) HSSB_FAIL(HSSB_ERR_STATE, "ULV factorisation: the generator pool is missing");
+  if (fpool_dev) { cudaFree(fpool_dev); fpool_dev = nullptr; }
+  factored = false;
   const size_t pool_b = (size_t)H->ulv_pool_len * sizeof(double);
-  if (cudaMalloc(&H->ulv_pool_dev, pool_b) != cudaSuccess) {
+  if (cudaMalloc(&fpool_dev, pool_b) != cudaSuccess) {
     cudaGetLastError();
-    H->ulv_pool_dev = nullptr;
+    fpool_dev = nullptr;
     HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of the %.3f GB ULV factor pool failed", pool_b * 1e-9);
   }
   const auto levels = ulv_levels(H);
@@ -370,7 +376,7 @@ static int ulv_factor_device(hssb_matrix* H) {
   if (e == cudaSuccess) e = cudaMalloc(&d_red, (size_t)H->ulv_red_len * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&d_scratch, scratch_doubles * sizeof(double));
   if (e == cudaSuccess) e = cudaMalloc(&d_piv, pivmin.size() * sizeof(double));
-  if (e == cudaSuccess) e = cudaMemsetAsync(H->ulv_pool_dev, 0, pool_b, H->stream);
+  if (e == cudaSuccess) e = cudaMemsetAsync(fpool_dev, 0, pool_b, H->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_nodes, H->ulv.data(), H->ulv.size() * sizeof(UlvNode), cudaMemcpyHostToDevice, H->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_piv, pivmin.data(), pivmin.size() * sizeof(double), cudaMemcpyHostToDevice, H->stream);
   std::vector<int32_t> flat;
@@ -382,7 +388,7 @@ static int ulv_factor_device(hssb_matrix* H) {
       const auto& l = levels[li];
       const LevelRun& r = runs[li];
       if (!l.empty()) {
-        UlvCtx cx{d_nodes, H->pool_dev, H->ulv_pool_dev, d_red, r.d.MI, r.d.NI, r.d.KR, r.d.KW, d_piv};
+        UlvCtx cx{d_nodes, gen_pool, fpool_dev, d_red, r.d.MI, r.d.NI, r.d.KR, r.d.KW, d_piv};
         const int grid = (int)std::min<size_t>(l.size(), (size_t)r.ctas);
         if (H->ulv_ff) ulv_factor_kernel_ff<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, r.stride);
         else ulv_factor_kernel<<<grid, 256, 0, H->stream>>>(cx, d_list + at, (int)l.size(), d_scratch, r.stride);
@@ -396,17 +402,17 @@ static int ulv_factor_device(hssb_matrix* H) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(H->stream);
   cleanup();
   if (e != cudaSuccess) {
-    cudaFree(H->ulv_pool_dev);
-    H->ulv_pool_dev = nullptr;
+    cudaFree(fpool_dev);
+    fpool_dev = nullptr;
     HSSB_FAIL(HSSB_ERR_CUDA, "ULV factorisation failed: %s", cudaGetErrorString(e));
   }
   const int64_t bad = ulv_first_breakdown(pivmin);
   if (bad >= 0) {  // do not keep (or cache) factors full of Inf / NaN
-    cudaFree(H->ulv_pool_dev);
-    H->ulv_pool_dev = nullptr;
+    cudaFree(fpool_dev);
+    fpool_dev = nullptr;
     HSSB_FAIL(HSSB_ERR_SINGULAR, "SingularException: the ULV factorisation met a zero pivot at node %lld (ulvfactor.jl:48 / :83)", (long long)bad);
   }
-  H->ulv_factored = true;
+  factored = true;
   return HSSB_OK;
 }
 

@@ -203,6 +203,18 @@ function HssMatrices.ulvfactsolve(p::PackedHss, B::StridedMatrix{Float64})
 end
 \(p::PackedHss, B::StridedMatrix{Float64}) = HssMatrices.ulvfactsolve(p, B)
 \(p::PackedHss, b::StridedVector{Float64}) = reshape(HssMatrices.ulvfactsolve(p, reshape(b, length(b), 1)), length(b))
+# A / hssB (src/hssmatrix.jl:236: ulvfactsolve(hssB', collect(A'))') without building hssB': uniform trees only
+# (second factor pool from the adjoint twin pool); other trees throw HssbError -- pack(hssB') and use `\` there.
+function Base.:/(A::StridedMatrix{Float64}, p::PackedHss)
+  size(A, 2) == size(p, 1) || throw(DimensionMismatch("Second dimension of A does not match first dimension of hssB."))
+  Bt = copy(A')
+  Z = Matrix{Float64}(undef, size(p, 1), size(Bt, 2))
+  GC.@preserve Bt Z begin
+    check(ccall((:hssb_solve_t, libhssb), Cint, (Ptr{Cvoid}, Int64, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Int64),
+      p.handle, size(Bt, 1), size(Bt, 2), pointer(Bt), max(size(Bt, 1), 1), pointer(Z), max(size(Z, 1), 1)))
+  end
+  return copy(Z')
+end
 """Factorise ahead of time (otherwise the first `\\` does it)."""
 ulvfactor!(p::PackedHss) = (check(ccall((:hssb_ulv_factor, libhssb), Cint, (Ptr{Cvoid},), p.handle)); p)
 

@@ -199,6 +199,13 @@ typedef struct hssb_ulv_info_t {
   int64_t flops_per_rhs; /* flops of one solve per right-hand-side column (factors x 8 B = bytes read / 2) */
   int64_t z_rows, f_rows; /* workspace rows of the solve                                        */
 } hssb_ulv_info_t;
+/* A' \ B, i.e. `/(A, hssB) = ulvfactsolve(hssB', collect(A'))'` (hssmatrix.jl:236) without building the adjoint
+ * matrix: on a uniform tree A' has the shapes of A, so the solve plan is shared and only a second factor pool is
+ * computed, from the adjoint twin pool (first call factorises; HSSB_ERR_STATE on trees without a twin pool: pack the
+ * adjoint there and use hssb_solve).  Z = A' \ B, so A / hssB = (hssb_solve_t(hssB, A'))'.                      */
+int hssb_solve_t(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* B, int64_t ldb, double* Z, int64_t ldz);
+int hssb_solve_t_dev(hssb_matrix* h, int64_t rows, int64_t nrhs, const double* dB, int64_t ldb, double* dZ, int64_t ldz,
+                     void* stream);
 int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
 
 /* Options. */

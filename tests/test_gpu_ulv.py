@@ -157,3 +157,29 @@ def test_singular_matrix_on_device(gpu, oracle):
         with pytest.raises(gpu.SingularException):
             P.ulv_factor()
         assert np.linalg.norm(P @ X) == 0.0
+
+
+@pytest.mark.parametrize("n,ls,r,k", [(4096, 128, 32, 9), (2048, 128, 16, 3), (4096, 256, 32, 40)])
+def test_right_division_by_the_adjoint_solve(gpu, oracle, ulv_oracle, n, ls, r, k):
+    """`/(A, hssB) = ulvfactsolve(hssB', collect(A'))'` (hssmatrix.jl:236) without building hssB': on a uniform tree
+    A' has the shapes of A, so hssb_solve_t shares the solve plan and factorises the adjoint twin pool."""
+    seed = 40 + r
+    h = oracle.synthetic_hss(n, ls, r, seed)
+    A = oracle.full(h)
+    B = oracle.synth_x(seed, n, k)
+    with gpu.synthetic(n, ls, r, seed) as P:
+        Zt = P.solve_t(B)                                   # A' \ B
+        assert np.linalg.norm(A.T @ Zt - B) <= 1e-13 * np.linalg.norm(A, 2) * np.linalg.norm(Zt)
+        ref = ulv_oracle.ulvfactsolve(oracle.adjoint(h), B)  # the reference's route: factorise the adjoint copy
+        assert np.linalg.norm(Zt - ref) <= 1e-14 * np.linalg.cond(A) * np.linalg.norm(ref)
+        M = B.T[:5].copy()                                  # a 5 x n matrix: M / hssB
+        Q = M / P
+        assert Q.shape == M.shape and np.linalg.norm(Q @ A - M) <= 1e-13 * np.linalg.norm(A, 2) * np.linalg.norm(Q)
+        Z = P.solve(B)                                      # the forward solve keeps its own factors
+        assert np.linalg.norm(A @ Z - B) <= 1e-13 * np.linalg.norm(A, 2) * np.linalg.norm(Z)
+        assert np.linalg.norm(P.solve_t(B) - Zt) == 0.0     # second call: cached factors, graph replay
+    rng = np.random.default_rng(1)
+    cl = oracle.bisection_cluster(300, 40)
+    with gpu.pack(to_product_tree(gpu, shifted(oracle, oracle.random_hss(cl, cl, rng, 1, 5), 20.0))) as G:
+        with pytest.raises(gpu.HssbError):                  # ragged tree: no twin pool
+            G.solve_t(np.zeros((300, 1)))
