@@ -120,3 +120,35 @@ def test_group_of_one_is_a_plain_handle(gpu, oracle):
         gpu.synthetic_group(n, ls, r, seed, [0, 0, 0, 0])     # more than two shards on one device
     with pytest.raises(gpu.HssbError):
         gpu.synthetic_group(128, 128, r, seed, [0, 0])        # tree too shallow for two shards
+
+
+def test_group_pipelined_host_entry_pageable_and_pinned(gpu, oracle):
+    """A call large enough to be pipelined over column blocks (every block carries its own exchange) and to be
+    staged through the pinned rings (pageable numpy memory), two shards in one process: against one GPU, bit for bit."""
+    import torch
+    n, ls, r, seed, k = 2 ** 17, 128, 32, 37, 64
+    X = oracle.synth_x(seed, n, k)
+    with gpu.synthetic(n, ls, r, seed) as single:
+        ref = single @ X
+    lazy = oracle.LazySyntheticHss(n, ls, r, seed)
+    for devs in device_sets(gpu, 2):
+        with gpu.synthetic_group(n, ls, r, seed, devs) as G:
+            Y = np.full((n, k), np.nan, order="F")
+            G.mul_(Y, X)                                    # pageable: rings + worker threads, 8 column blocks
+            assert all(sh.get_option(gpu.OPT_LAST_BOUNCE) == 3 for sh in G.shards)
+            assert np.array_equal(Y, ref), devs
+            Xh = torch.empty((k, n), dtype=torch.float64).pin_memory()
+            Yh = torch.empty((k, n), dtype=torch.float64).pin_memory()
+            Xh.numpy().T[:] = X
+            G.mul_(Yh.numpy().T, Xh.numpy().T)              # pinned: straight to the copy engines
+            assert all(sh.get_option(gpu.OPT_LAST_BOUNCE) == 0 for sh in G.shards)
+            assert np.array_equal(Yh.numpy().T, ref)
+    # and the single-GPU result itself against the oracle on a few leaves (sparse-support right-hand side)
+    s_lo, s_len = 3 * ls + 5, 2 * ls
+    Xs = np.random.default_rng(0).standard_normal((s_len, 4))
+    Xsp = np.zeros((n, 4))
+    Xsp[s_lo:s_lo + s_len] = Xs
+    with gpu.synthetic_group(n, ls, r, seed, device_sets(gpu, 2)[-1]) as G:
+        Ysp = G @ Xsp
+    for lo, yref in lazy.rows([0, 3 * ls, (n // ls // 2) * ls, n - ls], s_lo, Xs).items():
+        assert relerr(Ysp[lo:lo + ls], yref) <= TOL, lo
