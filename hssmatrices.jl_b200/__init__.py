@@ -61,6 +61,15 @@ class _TaskT(C.Structure):
         "ta0", "ta1", "sb0", "sb1", "sc", "epilogue")]
 
 
+class _BushOpT(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in (
+        "task", "bush", "level", "m0", "mr", "s0", "s1", "sc", "lds0", "lds1", "ldsc", "to_global", "sa0", "sa1")]
+
+
+class _BushStageT(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("bush", "kind", "src", "dst", "count", "ld", "level")]
+
+
 class _PhaseTime(C.Structure):
     _fields_ = [(n, C.c_int64) for n in (
         "kind", "level", "top", "fast", "ntasks", "flops_per_rhs", "gen_elems", "x_rows", "y_rows")] + [("ms", C.c_double)]
@@ -123,6 +132,11 @@ SIGNATURES = {
     "hssb_debug_pool": (C.c_int, [_P, _P, _i64]),
     "hssb_debug_pool_t": (C.c_int, [_P, _P, _i64]),
     "hssb_debug_tree_trace": (C.c_int, [_P, _i64, _P, C.c_int]),
+    "hssb_debug_bush_counts": (C.c_int, [_P, C.c_int, C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64), C.POINTER(_i64)]),
+    "hssb_debug_bush_op": (C.c_int, [_P, C.c_int, _i64, C.POINTER(_BushOpT)]),
+    "hssb_debug_bush_deps": (_i64, [_P, C.c_int, _i64, _P, _i64]),
+    "hssb_debug_bush_stage": (_i64, [_P, C.c_int, _i64, C.POINTER(_BushStageT)]),
+    "hssb_debug_bush_trace": (_i64, [_P, C.c_int, _P, _i64]),
     "hssb_ulv_factor": (C.c_int, [_P]),
     "hssb_solve": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64]),
     "hssb_solve_dev": (C.c_int, [_P, _i64, _i64, _P, _i64, _P, _i64, _P]),
@@ -143,7 +157,7 @@ SIGNATURES = {
     "hssb_group_sync": (C.c_int, [_P]),
 }
 
-OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS, OPT_ADJOINT_TWIN, OPT_ULV_FAST, OPT_TREE_KERNEL, OPT_HOST_BOUNCE, OPT_LAST_BOUNCE, OPT_LEAF_KERNEL, OPT_LEAF_FUSION, OPT_FLOW_KERNEL, OPT_HOST_THREADS = 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15
+OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS, OPT_ADJOINT_TWIN, OPT_ULV_FAST, OPT_TREE_KERNEL, OPT_HOST_BOUNCE, OPT_LAST_BOUNCE, OPT_LEAF_KERNEL, OPT_LEAF_FUSION, OPT_FLOW_KERNEL, OPT_HOST_THREADS, OPT_BUSH_KERNEL, OPT_BUSH_LEVELS = 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17
 PHASE_NAMES = ("leaf_up", "merge", "exchange", "translate", "leaf_down", "exchange_ack")
 KIND_NAMES = ("D", "U", "V", "B12", "B21", "R", "W")
 
@@ -818,6 +832,38 @@ class PackedHss:
         pool = np.zeros(pl.value)
         _check(lib().hssb_debug_pool_t(self._h, _ptr(pool), pool.size))
         return pool
+
+    def debug_bush_plan(self, mode=0):
+        """The bush plan (csrc/hssb_bush.cuh) of the product (mode 0) or of the transposed task table (mode 1):
+        (ops, deps per bush, shared-memory doubles per CTA, staged copies)."""
+        nb, no, nd, sm = _i64(), _i64(), _i64(), _i64()
+        _check(lib().hssb_debug_bush_counts(self._h, mode, C.byref(nb), C.byref(no), C.byref(nd), C.byref(sm)))
+        ops = []
+        for i in range(no.value):
+            o = _BushOpT()
+            _check(lib().hssb_debug_bush_op(self._h, mode, i, C.byref(o)))
+            ops.append(o)
+        deps = []
+        for b in range(nb.value):
+            buf = np.zeros(max(nd.value, 1), dtype=np.int64)
+            n = _check(lib().hssb_debug_bush_deps(self._h, mode, b, _ptr(buf), buf.size))
+            deps.append([int(x) for x in buf[:n]])
+        stages = []
+        for i in range(_check(lib().hssb_debug_bush_stage(self._h, mode, 0, None))):
+            st = _BushStageT()
+            _check(lib().hssb_debug_bush_stage(self._h, mode, i, C.byref(st)))
+            stages.append(st)
+        return ops, deps, sm.value, stages
+
+    def debug_bush_trace(self, mode=0, items=None):
+        """Timeline of the last bush-kernel launch (diagnostics): None switches recording on; afterwards an
+        (items, 12) array: SM, ns drawn, ns dependencies met, ns end of levels 0..7, ns flag published."""
+        if items is None:
+            _check(lib().hssb_debug_bush_trace(self._h, mode, None, 0))
+            return None
+        buf = np.zeros((items, 12), dtype=np.uint64)
+        n = _check(lib().hssb_debug_bush_trace(self._h, mode, _ptr(buf), items))
+        return buf[:n]
 
     def debug_plan(self):
         nt, nph, pl = _i64(), _i64(), _i64()

@@ -229,6 +229,7 @@ static void fill_pool_host(hssb_matrix* H, const std::vector<BlockSource>* src) 
 #include "hssb_xchg.cuh"
 #include "hssb_tree.cuh"
 #include "hssb_flow.cuh"
+#include "hssb_bush.cuh"
 #include "hssb_hostpipe.h"
 namespace hssb {
 
@@ -259,6 +260,17 @@ static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
   const std::vector<Phase>& phases = phase_list(H, cp.trans);
   const bool prof = H->profile;
   // any-shape plans (no fixed-shape kernel applies): the whole product as one dataflow launch (hssb_flow.cuh)
+  // ... small trees as one launch over whole bushes of the tree (hssb_bush.cuh)
+  if (bush_usable(H, cp.trans) && plan_runs_generic(H, cp)) {  // leaf-up launch, every level in between as one launch, leaf-down launch
+    bool tree_done = false;
+    for (const Phase& ph : phases) {
+      int rc = HSSB_OK;
+      if (ph.kind == PH_LEAF_UP || ph.kind == PH_LEAF_DOWN) rc = launch_generic(H, ph, cp, st);
+      else if (!tree_done) { rc = launch_bush(H, cp.trans, cp, st); tree_done = true; }
+      if (rc) return rc;
+    }
+    return HSSB_OK;
+  }
   if (flow_usable(H, cp.trans) && plan_runs_generic(H, cp)) return launch_flow(H, cp.trans, cp, st);
   if (prof) {
     H->prof_mode = cp.trans;
@@ -571,13 +583,14 @@ int hssb_synthetic_rhs(uint64_t seed, int64_t n, int64_t nrhs, int64_t row0, int
 int hssb_destroy(hssb_matrix* h) {
   return guarded<int>([&]() -> int {
   if (!h) return HSSB_OK;
-  if (h->device < 0) { delete h; return HSSB_OK; }
+  if (h->device < 0) { free_bush(h); delete h; return HSSB_OK; }
   DeviceGuard dg(h->device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   invalidate_graphs(h);
   free_fast(h);
   free_tree(h);
   free_flow(h);
+  free_bush(h);
   for (auto e : h->prof_events) cudaEventDestroy(e);
   if (h->nccl_comm && g_nccl.CommDestroy) g_nccl.CommDestroy(h->nccl_comm);
   for (int r = 0; r < hssb_matrix::MAX_PEERS; ++r)
@@ -750,6 +763,10 @@ static int matmul_dev_impl(hssb_matrix* h, int trans, int64_t rows_y, int64_t ro
   }
   if (h->flow_kernel && trans <= 1 && h->n_shards == 1) {  // likewise
     rc = ensure_flow_plan(h, trans, nrhs);
+    if (rc) return rc;
+  }
+  if (h->bush_kernel && trans <= 1 && h->n_shards == 1 && (h->bush_kernel >= 2 || bush_eligible(h))) {
+    rc = ensure_bush_plan(h, trans, nrhs);
     if (rc) return rc;
   }
   cudaStream_t st = (cudaStream_t)stream;  // NULL = the CUDA default stream, as everywhere in CUDA
@@ -1048,6 +1065,23 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
       break;
     case HSSB_OPT_LEAF_FUSION: h->leaf_fusion = value != 0; break;
     case HSSB_OPT_FLOW_KERNEL: h->flow_kernel = value != 0; break;
+    case HSSB_OPT_BUSH_KERNEL:
+      if (value < 0 || value > 2) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_BUSH_KERNEL: 0, 1 or 2");
+      h->bush_kernel = (int)value;
+      break;
+    case HSSB_OPT_BUSH_LEVELS: {
+      const int hb = (int)(value / 16), hb0 = (int)(value % 16);
+      if (value < 0 || hb < 1 || hb > 15) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_BUSH_LEVELS: levels per bush (1-15) * 16 + leaf-bush levels (0-15)");
+      h->bush_levels = hb; h->bush_levels0 = hb0;
+      if (h->device >= 0) {
+        DeviceGuard dgb(h->device);
+        if (h->stream) cudaStreamSynchronize(h->stream);
+        free_bush(h);
+      } else {
+        free_bush(h);
+      }
+      break;
+    }
     case HSSB_OPT_HOST_BOUNCE:
       if (value < 0 || value > 2) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_HOST_BOUNCE: 0, 1 or 2");
       h->host_bounce = (int)value;
@@ -1092,6 +1126,12 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
       const FlowPlan* fp = (const FlowPlan*)h->flow_plan[0];
       return fp && fp->usable ? 2 : 1;  // 2: the product plan qualifies and has been set up
     }
+    case HSSB_OPT_BUSH_KERNEL: {
+      if (!h->bush_kernel) return 0;
+      const BushPlan* bp = (const BushPlan*)h->bush_plan[0];
+      return bp && bp->usable && bp->sync_dev && (h->bush_kernel >= 2 || bush_eligible(h)) ? 3 : h->bush_kernel;
+    }
+    case HSSB_OPT_BUSH_LEVELS: return h->bush_levels * 16 + h->bush_levels0;
     case HSSB_OPT_LAST_BOUNCE: return h->last_bounce;
     case HSSB_OPT_HOST_THREADS: return host_pool(0).size();
     default: return -1;
@@ -1334,6 +1374,90 @@ int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len) {
 
 // Host image of the adjoint twin pool (what ensure_twin builds on the device), for plan-only and
 // device handles alike: CPU tests run the FORWARD plan over it and must obtain A' X.
+static BushPlan* debug_bush_plan(hssb_matrix* h, int mode) {
+  if (!h || mode < 0 || mode > 1) { set_error("hssb_debug_bush: bad argument"); return nullptr; }
+  BushPlan* bp = (BushPlan*)h->bush_plan[mode];
+  if (!bp) {  // host part only: works on plan-only handles
+    bp = new (std::nothrow) BushPlan();
+    if (!bp) { set_error("hssb_debug_bush: out of memory"); return nullptr; }
+    bush_plan_host(h, mode, h->bush_levels, h->bush_levels0, BUSH_SMEM_BUDGET, *bp);
+    if (h->device >= 0) { delete bp; bp = nullptr; }  // device handles build (and upload) theirs at the first product
+    else h->bush_plan[mode] = bp;
+    if (!bp) {
+      DeviceGuard dg(h->device);
+      if (ensure_bush_plan(h, mode, 1) != HSSB_OK) return nullptr;
+      bp = (BushPlan*)h->bush_plan[mode];
+    }
+  }
+  if (bp && !bp->usable) { set_error("hssb_debug_bush: no bush plan: %s", bp->why.c_str()); return nullptr; }
+  return bp;
+}
+
+int hssb_debug_bush_counts(hssb_matrix* h, int mode, int64_t* n_bush, int64_t* n_ops, int64_t* n_deps, int64_t* smem_doubles) {
+  return guarded<int>([&]() -> int {
+  const BushPlan* bp = debug_bush_plan(h, mode);
+  if (!bp) return HSSB_ERR_STATE;
+  if (n_bush) *n_bush = bp->nbush;
+  if (n_ops) *n_ops = (int64_t)bp->ops.size();
+  if (n_deps) *n_deps = (int64_t)bp->deps.size();
+  if (smem_doubles) *smem_doubles = bp->smem_doubles;
+  return HSSB_OK;
+  });
+}
+
+int hssb_debug_bush_op(hssb_matrix* h, int mode, int64_t i, hssb_bush_op_t* o) {
+  return guarded<int>([&]() -> int {
+  const BushPlan* bp = debug_bush_plan(h, mode);
+  if (!bp) return HSSB_ERR_STATE;
+  if (!o || i < 0 || i >= (int64_t)bp->ops.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_bush_op: bad argument");
+  const BushOp& b = bp->ops[(size_t)i];
+  o->task = bp->task0 + bp->op_task[(size_t)i]; o->bush = bp->op_bush[(size_t)i]; o->level = bp->op_level[(size_t)i];
+  o->m0 = b.m0; o->mr = b.mr; o->s0 = b.s0; o->s1 = b.s1; o->sc = b.sc_off;
+  o->lds0 = b.lds0; o->lds1 = b.lds1; o->ldsc = b.ldsc; o->to_global = b.to_global;
+  o->sa0 = b.sa0; o->sa1 = b.sa1;
+  return HSSB_OK;
+  });
+}
+
+int64_t hssb_debug_bush_trace(hssb_matrix* h, int mode, uint64_t* out, int64_t cap_items) {
+  return guarded<int64_t>([&]() -> int64_t {
+  if (!h || mode < 0 || mode > 1 || h->device < 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_bush_trace: bad argument");
+  if (!out) { h->bush_trace = true; return 0; }
+  DeviceGuard dg(h->device);
+  const BushPlan* bp = (const BushPlan*)h->bush_plan[mode];
+  if (!bp || !bp->trace_dev) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_bush_trace: nothing recorded (switch it on, then run a product)");
+  if (h->stream) HSSB_CUDA(cudaStreamSynchronize(h->stream));
+  HSSB_CUDA(cudaDeviceSynchronize());
+  const int64_t items = std::min<int64_t>(cap_items, (int64_t)bp->nbush * bp->sync_cols);
+  HSSB_CUDA(cudaMemcpy(out, bp->trace_dev, (size_t)items * B_TRACE * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  return items;
+  });
+}
+
+int64_t hssb_debug_bush_stage(hssb_matrix* h, int mode, int64_t i, hssb_bush_stage_t* o) {
+  return guarded<int64_t>([&]() -> int64_t {
+  const BushPlan* bp = debug_bush_plan(h, mode);
+  if (!bp) return HSSB_ERR_STATE;
+  if (!o) return (int64_t)bp->stages.size();
+  if (i < 0 || i >= (int64_t)bp->stages.size()) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_bush_stage: bad argument");
+  const BushStage& st = bp->stages[(size_t)i];
+  o->bush = bp->stage_bush[(size_t)i]; o->kind = st.kind; o->src = st.src; o->dst = st.dst; o->count = st.count; o->ld = st.ld;
+  o->level = 0;
+  return (int64_t)bp->stages.size();
+  });
+}
+
+int64_t hssb_debug_bush_deps(hssb_matrix* h, int mode, int64_t b, int64_t* out, int64_t cap) {
+  return guarded<int64_t>([&]() -> int64_t {
+  const BushPlan* bp = debug_bush_plan(h, mode);
+  if (!bp) return HSSB_ERR_STATE;
+  if (b < 0 || b >= bp->nbush) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_bush_deps: bad argument");
+  const BushHdr& hd = bp->hdr[(size_t)b];
+  for (int64_t d = 0; d < hd.ndeps && d < cap && out; ++d) out[d] = bp->deps[(size_t)(hd.dep0 + d)];
+  return hd.ndeps;
+  });
+}
+
 int hssb_debug_pool_t(const hssb_matrix* h, double* out, int64_t len) {
   return guarded<int>([&]() -> int {
   if (!h || !out) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_pool_t: NULL argument");

@@ -251,5 +251,11 @@ struct hssb_matrix {
   // HSSB_OPT_FLOW_KERNEL: any-shape plans of single-shard handles run as ONE persistent dataflow kernel (hssb_flow.cuh)
   int flow_kernel = 1;
   void* flow_plan[2] = {nullptr, nullptr};  // [0] Y = A X, [1] Y = A' X on the any-shape task table
+  // HSSB_OPT_BUSH_KERNEL: small any-shape trees (64-row leaves, ranks <= 64: what a compression produces) run as ONE launch
+  // whose items are whole bushes of the tree (hssb_bush.cuh).  0 off, 1 automatic (eligible trees), 2 whenever a plan exists
+  int bush_kernel = 1;
+  int bush_levels = 3, bush_levels0 = 2;    // HSSB_OPT_BUSH_LEVELS: levels per bush / levels of the bushes that hold the leaves
+  void* bush_plan[2] = {nullptr, nullptr};
+  bool bush_trace = false;                  // hssb_debug_bush_trace: the kernel records a timeline per item
   void* tree_plan = nullptr;
 };

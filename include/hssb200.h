@@ -250,6 +250,13 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
                                     the 2*depth+2 dependent levels cost a flag round trip each instead of a launch (csrc/hssb_flow.cuh).
                                     Single-shard handles, product and transposed product.  0: one launch per level.  hssb_get_option
                                     returns 2 once the product plan has been set up for it                                          */
+#define HSSB_OPT_BUSH_KERNEL 16  /* 1 (default): SMALL any-shape trees (leaves of at most 64 rows / columns, ranks <= 64, at most 16384
+                                    leaves: BASELINE configs 1-2) run the whole product in one launch whose work items are BUSHES -- the
+                                    tasks of a few consecutive levels below one node -- executed by one CTA with the intermediate Z / F
+                                    blocks in shared memory; the dependent chain of config 2 is 7 flag round trips instead of 22 levels
+                                    (csrc/hssb_bush.cuh).  Takes precedence over HSSB_OPT_FLOW_KERNEL where it applies.  2: any
+                                    single-shard any-shape plan.  0: off.  hssb_get_option returns 3 once the product plan runs on it   */
+#define HSSB_OPT_BUSH_LEVELS 17  /* levels per bush * 16 + levels of the bushes that hold the leaves (default 3 * 16 + 2); rebuilds the plan */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
@@ -352,6 +359,31 @@ int hssb_debug_pool(const hssb_matrix* h, double* out, int64_t len);
  * current workspace contents; returns the number of steps written (<= cap) or a negative status.               */
 int hssb_debug_tree_trace(hssb_matrix* h, int64_t nrhs, double* us_out, int cap);
 int hssb_debug_pool_t(const hssb_matrix* h, double* out, int64_t len); /* image of the adjoint twin pool */
+/* The bush plan (csrc/hssb_bush.cuh) of plan-only or device handles, for the numpy interpreter: mode 0 = product,
+ * 1 = transposed task table.  An op is one warp's work: rows [m0, m0 + mr) of task `task` (index into
+ * hssb_debug_task), executed in level `level` of bush `bush`; s0 / s1 / sc >= 0: the operand / output block has a
+ * shared-memory image at that offset (doubles) with leading dimension lds0 / lds1 / ldsc.                        */
+typedef struct hssb_bush_op_t {
+  int64_t task, bush, level, m0, mr;
+  int64_t s0, s1, sc, lds0, lds1, ldsc, to_global;
+  int64_t sa0, sa1; /* >= 0: the A block is read from a staged shared-memory copy of the generator block */
+} hssb_bush_op_t;
+/* A staged copy into shared memory at `dst` when the bush starts: kind 0 = `count` doubles of the pool from offset src;
+ * 1 = Z, 2 = F: one 16-column tile of the workspace block at row src (count = ld * 16); 3 = rows [src, src + count) of
+ * the column tile of X with leading dimension ld; 4 = the bush's ops.  Everything has landed before level 0.        */
+typedef struct hssb_bush_stage_t {
+  int64_t bush, kind, src, dst, count, ld, level;
+} hssb_bush_stage_t;
+int hssb_debug_bush_counts(hssb_matrix* h, int mode, int64_t* n_bush, int64_t* n_ops, int64_t* n_deps, int64_t* smem_doubles);
+/* Diagnostics: timeline of the last bush-kernel launch.  hssb_debug_bush_trace(h, mode, NULL, 0) switches recording on (the
+ * next call re-allocates the flags with a trace buffer); with `out` it copies 12 words per item (bush-major, then column
+ * tile): SM, then globaltimer ns when the item was drawn, its dependencies were met, levels 0..7 ended, its flag was
+ * published.  Returns the number of items written or a negative status.                                                */
+int64_t hssb_debug_bush_trace(hssb_matrix* h, int mode, uint64_t* out, int64_t cap_items);
+int64_t hssb_debug_bush_stage(hssb_matrix* h, int mode, int64_t i, hssb_bush_stage_t* out); /* returns the number of stages */
+int hssb_debug_bush_op(hssb_matrix* h, int mode, int64_t i, hssb_bush_op_t* out);
+/* dependencies of bush b: returns their count, writes at most cap bush indices */
+int64_t hssb_debug_bush_deps(hssb_matrix* h, int mode, int64_t b, int64_t* out, int64_t cap);
 /* ULV: factorise a plan-only handle on the host with the device's node routine (single-thread team),
  * and read the factor pool (either kind of handle) for the numpy plan interpreter.                   */
 int hssb_debug_ulv_factor_host(hssb_matrix* h);

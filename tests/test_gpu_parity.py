@@ -483,6 +483,7 @@ def test_dataflow_kernel_any_shape_trees(gpu, oracle, n, leafsize, nrhs, rmin, r
     tree = to_product_tree(gpu, h)
     P = tree.repack()
     P.set_option(gpu.OPT_PIPELINE_COLS, 1 << 20)      # one column block per host call: launches are countable
+    P.set_option(gpu.OPT_BUSH_KERNEL, 0)              # small trees would go to the bush kernel (next test)
     P.set_option(gpu.OPT_FLOW_KERNEL, 0)
     l0 = P.launch_count()
     Y0 = P @ X
@@ -505,6 +506,60 @@ def test_dataflow_kernel_any_shape_trees(gpu, oracle, n, leafsize, nrhs, rmin, r
     assert relerr(got, oracle.mul(C0.copy(), h, X, 0.7, -1.3)) <= TOL
     X2 = rng.standard_normal((n, 2 * nrhs + 1))       # more column tiles than before: the counters grow
     assert relerr(P @ X2, oracle.matmul(h, X2)) <= TOL
+    P.close()
+
+
+@pytest.mark.parametrize("n,leafsize,nrhs,rmin,rmax,levels", [
+    (2001, 64, 16, 9, 20, 50), (777, 50, 5, 1, 9, 50), (4096, 64, 64, 13, 40, 50), (4096, 64, 33, 13, 20, 33), (300, 40, 3, 0, 2, 16),
+    (4000, 128, 130, 5, 40, 50), (3000, 40, 17, 0, 12, 83)])
+def test_bush_kernel_small_trees(gpu, oracle, n, leafsize, nrhs, rmin, rmax, levels):
+    """Small any-shape trees (BASELINE configs 1-2): every merge / translate level between the two leaf launches
+    runs as ONE launch over whole bushes of the tree (HSSB_OPT_BUSH_KERNEL, csrc/hssb_bush.cuh): a few levels of
+    matmul.jl:39 / :52-56 per CTA out of shared memory, warp-sized DMMA tasks.  Same k order and the same DMMA as
+    the any-shape tile kernel but four interleaved accumulator sets (a warp working alone is bound by the latency of a
+    dependent DMMA): agrees with one launch per level to rounding, and with itself bit for bit; also A' X on the
+    transposed task table, alpha / beta, repeated calls, other cuts of the tree (HSSB_OPT_BUSH_LEVELS) and, forced (= 2), a tree
+    with 128-row leaves."""
+    rng = np.random.default_rng(n + nrhs)
+    rcl = oracle.bisection_cluster(n, leafsize)
+    h = oracle.random_hss(rcl, rcl, rng, rmin, rmax)
+    X = rng.standard_normal((n, nrhs))
+    ref = oracle.matmul(h, X)
+    P = to_product_tree(gpu, h).repack()
+    P.set_option(gpu.OPT_PIPELINE_COLS, 1 << 20)
+    P.set_option(gpu.OPT_BUSH_KERNEL, 0)
+    P.set_option(gpu.OPT_FLOW_KERNEL, 0)
+    l0 = P.launch_count()
+    Y0 = P @ X
+    per_level = P.launch_count() - l0
+    T0 = P.tmatmul(X)
+    eligible = leafsize <= 64
+    P.set_option(gpu.OPT_BUSH_KERNEL, 1 if eligible else 2)
+    P.set_option(gpu.OPT_BUSH_LEVELS, levels)
+    for _ in range(3):
+        l0 = P.launch_count()
+        Y1 = P @ X
+        assert P.launch_count() - l0 <= 3 < per_level      # leaf-up, the bushes, leaf-down
+        assert relerr(Y1, Y0) <= 1e-14 and (_ == 0 or np.array_equal(Y1, Yp))
+        Yp = Y1
+    assert P.get_option(gpu.OPT_BUSH_KERNEL) == 3
+    assert relerr(Y1, ref) <= TOL
+    l0 = P.launch_count()
+    T1 = P.tmatmul(X)
+    assert P.launch_count() - l0 <= 3
+    assert relerr(T1, T0) <= 1e-14 and relerr(T1, oracle.matmul(oracle.adjoint(h), X)) <= TOL
+    C0 = rng.standard_normal((n, nrhs))
+    got = P.mul_(np.asfortranarray(C0.copy()), X, 0.7, -1.3)
+    assert relerr(got, oracle.mul(C0.copy(), h, X, 0.7, -1.3)) <= TOL
+    got = P.mul_(np.full((n, nrhs), np.nan, order="F"), X, 2.0, 0.0)   # beta == 0 never reads C
+    assert np.isfinite(got).all() and relerr(got, 2.0 * ref) <= TOL
+    X2 = rng.standard_normal((n, 2 * nrhs + 1))       # more column tiles than before: the flags grow
+    assert relerr(P @ X2, oracle.matmul(h, X2)) <= TOL
+    P.set_option(gpu.OPT_BUSH_LEVELS, 2 * 16 + 1)     # another cut of the same tree: plan rebuilt
+    assert relerr(P @ X, Y0) <= 1e-14
+    if not eligible:
+        P.set_option(gpu.OPT_BUSH_KERNEL, 1)          # automatic: 128-row leaves stay on the dataflow kernel
+        assert np.array_equal(P @ X, Y0) and P.get_option(gpu.OPT_BUSH_KERNEL) == 1
     P.close()
 
 

@@ -82,6 +82,57 @@ def test_rectangular_and_unbalanced(hb, oracle):
     assert relerr(Y, ref) <= TOL
 
 
+BUSH_CASES = [c for c in CASES if c[0] > c[1] * 2] + [(4096, 64, 20, 9, 20), (3000, 40, 33, 0, 12)]   # trees with at least one merge level
+
+
+@pytest.mark.parametrize("levels", [3 * 16 + 2, 2 * 16 + 1, 1 * 16 + 0, 5 * 16 + 3])
+@pytest.mark.parametrize("n,leafsize,nrhs,rmin,rmax", BUSH_CASES)
+def test_bush_plan_matches_oracle(hb, oracle, n, leafsize, nrhs, rmin, rmax, levels):
+    """The bush plan of small any-shape trees (csrc/hssb_bush.cuh: a few levels of the recursion of
+    matmul.jl:32-62 per work item, intermediate blocks in shared memory), executed by the numpy interpreter
+    with the kernel's visibility rules, for the product and for the transposed task table."""
+    rng = np.random.default_rng(n * 11 + leafsize)
+    cl = oracle.bisection_cluster(n, leafsize)
+    h = oracle.random_hss(cl, cl, rng, rmin, rmax)
+    X = rng.standard_normal((n, nrhs))
+    ref = oracle.matmul(h, X)
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    P.set_option(hb.OPT_BUSH_LEVELS, levels)
+    assert P.get_option(hb.OPT_BUSH_LEVELS) == levels
+    C0 = rng.standard_normal((n, nrhs))
+    Y = np.asfortranarray(C0.copy())
+    _, st = plan_interp.run_bush_plan(P, X, Y, 0.7, -1.3)
+    assert relerr(Y, 0.7 * ref - 1.3 * C0) <= TOL
+    depth = int(P.info.depth)
+    if depth >= 6 and levels == 3 * 16 + 2:
+        assert st["chain"] <= 2 * ((depth + 2) // 3) + 1 < 2 * depth   # the point of the exercise
+        assert st["staged_a"] == st["staged_b"] == st["ops"]              # nothing on a bush's critical path reads global memory
+    Y = np.full((n, nrhs), np.nan, order="F")
+    plan_interp.run_bush_plan(P, X, Y, trans=True)
+    assert relerr(Y, oracle.matmul(oracle.adjoint(h), X)) <= TOL
+
+
+def test_bush_plan_rectangular_and_unbalanced(hb, oracle):
+    rng = np.random.default_rng(11)
+    rcl = oracle.bisection_cluster(2000, 70)
+    ccl = oracle.bisection_cluster(1332, 47)  # same tree shape (32 leaves), different sizes
+    h = oracle.random_hss(rcl, ccl, rng, 1, 7)
+    h.A11 = oracle.prune_leaves(h.A11)
+    h.sz1 = oracle.size(h.A11)
+    h.A22.A11 = oracle.prune_leaves(h.A22.A11)
+    h.A22.sz1 = oracle.size(h.A22.A11)
+    X = rng.standard_normal((1332, 6))
+    ref = oracle.full(h) @ X
+    P = hb.pack(to_product_tree(hb, h), plan_only=True)
+    Y = np.full((2000, 6), np.nan, order="F")
+    plan_interp.run_bush_plan(P, X, Y)
+    assert relerr(Y, ref) <= TOL
+    Xt = rng.standard_normal((2000, 4))
+    Yt = np.full((1332, 4), np.nan, order="F")
+    plan_interp.run_bush_plan(P, Xt, Yt, trans=True)
+    assert relerr(Yt, oracle.full(h).T @ Xt) <= TOL
+
+
 @pytest.mark.parametrize("n,leafsize,nrhs,rmin,rmax", CASES[:5])
 def test_transposed_plan(hb, oracle, n, leafsize, nrhs, rmin, rmax):
     """Y = A' X on the same packed generators == product with the reference's copied adjoint
