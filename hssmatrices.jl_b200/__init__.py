@@ -855,15 +855,16 @@ class PackedHss:
             stages.append(st)
         return ops, deps, sm.value, stages
 
-    def debug_bush_trace(self, mode=0, items=None):
+    def debug_bush_trace(self, mode=0, items=None, probe_item=0):
         """Timeline of the last bush-kernel launch (diagnostics): None switches recording on; afterwards an
         (items, 12) array: SM, ns drawn, ns dependencies met, ns end of levels 0..7, ns flag published."""
         if items is None:
-            _check(lib().hssb_debug_bush_trace(self._h, mode, None, 0))
+            _check(lib().hssb_debug_bush_trace(self._h, mode, None, probe_item))
             return None
-        buf = np.zeros((items, 12), dtype=np.uint64)
-        n = _check(lib().hssb_debug_bush_trace(self._h, mode, _ptr(buf), items))
-        return buf[:n]
+        buf = np.zeros((items + 43, 12), dtype=np.uint64)   # + the probe block: 8 levels x 8 warps x 8 cycle stamps
+        n = _check(lib().hssb_debug_bush_trace(self._h, mode, _ptr(buf), items + 43))
+        self.bush_probe = buf[items:].reshape(-1)[:512].reshape(8, 8, 8).astype(np.int64)
+        return buf[:min(n, items)]
 
     def debug_plan(self):
         nt, nph, pl = _i64(), _i64(), _i64()

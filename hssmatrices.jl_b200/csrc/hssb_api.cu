@@ -1422,14 +1422,17 @@ int hssb_debug_bush_op(hssb_matrix* h, int mode, int64_t i, hssb_bush_op_t* o) {
 int64_t hssb_debug_bush_trace(hssb_matrix* h, int mode, uint64_t* out, int64_t cap_items) {
   return guarded<int64_t>([&]() -> int64_t {
   if (!h || mode < 0 || mode > 1 || h->device < 0) HSSB_FAIL(HSSB_ERR_ARG, "hssb_debug_bush_trace: bad argument");
-  if (!out) { h->bush_trace = true; return 0; }
+  if (!out) { h->bush_trace = true; h->bush_probe_item = (int)cap_items; return 0; }   // cap_items doubles as the item to probe
   DeviceGuard dg(h->device);
   const BushPlan* bp = (const BushPlan*)h->bush_plan[mode];
   if (!bp || !bp->trace_dev) HSSB_FAIL(HSSB_ERR_STATE, "hssb_debug_bush_trace: nothing recorded (switch it on, then run a product)");
   if (h->stream) HSSB_CUDA(cudaStreamSynchronize(h->stream));
   HSSB_CUDA(cudaDeviceSynchronize());
-  const int64_t items = std::min<int64_t>(cap_items, (int64_t)bp->nbush * bp->sync_cols);
+  const int64_t all = (int64_t)bp->nbush * bp->sync_cols;
+  const int64_t items = std::min<int64_t>(cap_items, all);
   HSSB_CUDA(cudaMemcpy(out, bp->trace_dev, (size_t)items * B_TRACE * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+  if (cap_items >= all + (B_PROBE_LEVELS * B_WARPS * 8 + B_TRACE - 1) / B_TRACE)   // room for the probe block behind the items
+    HSSB_CUDA(cudaMemcpy(out + all * B_TRACE, bp->trace_dev + all * B_TRACE, (size_t)B_PROBE_LEVELS * B_WARPS * 8 * sizeof(unsigned long long), cudaMemcpyDeviceToHost));
   return items;
   });
 }

@@ -14,9 +14,9 @@
 //   * the CTA then runs the item level by level with a __syncthreads in between; Z / F blocks that are produced and
 //     consumed inside the bush never leave shared memory unless somebody outside needs them;
 //   * only bushes talk through global flags: 7 dependent steps for config 2 instead of 20;
-//   * the unit of work is a WARP: up to 32 rows x 16 right-hand sides of one task with DMMA m8n8k4, fragments read
-//     straight from the shared-memory images -- no barrier inside a task, so a level of eight small blocks is eight
-//     independent warps.
+//   * the unit of work is a WARP: 8 rows x 16 right-hand sides of one task, operands read straight from the
+//     shared-memory images -- no barrier inside a task, so a level of eight small blocks is 24 independent warp tasks.
+//     They run on the FP64 FMA pipe, not on DMMA: a warp that works alone waits ~500 cycles for a dependent DMMA.
 // The leaf phases stay on the tile kernel (they are throughput work on 64-row blocks): leaf-up launch, this kernel,
 // leaf-down launch.  Items (bush, 16-column tile) are drawn in a topological order of the bushes from one atomic
 // counter by the resident CTAs, as in hssb_flow.cuh: a CTA only waits for items drawn before its own, so there is no
@@ -44,7 +44,7 @@ struct BushOp {            // one warp's work: rows [m0, m0 + mr) of one task, o
   int64_t a0, a1;          // pool offsets of the two A operands (whole block)
   int64_t b0, b1, c;       // global operands as in GTask: X / Y first row, or workspace row offset
   int32_t lda0, lda1, ldb0, ldb1, ldc;
-  int32_t m0, mr;          // row chunk, mr <= 16
+  int32_t m0, mr;          // row chunk, mr <= 8
   int32_t K0, K1;
   int32_t s0, s1, sc_off;  // shared-memory image of B0 / B1 / the output block (offset in doubles), -1: none
   int32_t lds0, lds1, ldsc;
@@ -83,7 +83,9 @@ struct BushParams {
   unsigned int* sync;      // [0] = next item, [1 + bush * ncol + coltile] = done
   int32_t nbush;
   unsigned long long* trace;  // diagnostics (hssb_debug_bush_trace): B_TRACE words per item, or NULL
+  int32_t probe_item;         // ... and cycle stamps inside the ops of this item, after the per-item words
 };
+constexpr int B_PROBE_LEVELS = 8;
 
 constexpr int B_TRACE = 12;   // item: [0] SM, [1] drawn, [2] dependencies met, [3 .. 3 + 7] end of level l, [11] flag published (ns, globaltimer)
 __device__ __forceinline__ unsigned long long bush_now() {
@@ -92,29 +94,28 @@ __device__ __forceinline__ unsigned long long bush_now() {
   return t;
 }
 
-// One warp, one op: up to 16 rows x 16 right-hand sides of one task.  Two things bound a warp that works alone:
-//   * the latency of a DEPENDENT DMMA (a few hundred cycles): consecutive k-steps therefore go to FOUR accumulator sets
-//     (k-step t of an operand to set t mod 4), summed at the end -- a rank-17 merge is a chain of 3 DMMAs, not 10.  The
-//     order of the additions differs from the tile kernel's, so the two agree to rounding, not bit for bit;
-//   * the latency of its own instruction stream: the per-op code is one loop shared by both operands and both A
-//     layouts (run-time strides), 4 k-steps per trip, everything it reads already in shared memory.
-// A workspace block that could not be staged is read with ld.global.cg: it was written in this launch by another SM and
-// must not come from a stale L1 line.  (Volatile loads for both cases were tried: they compile to LD.STRONG.SYS, which
-// serialises, and cost more than everything else in the op.)
-__device__ __forceinline__ void bush_warp_op(const BushOp& o, const CallParams& p, double* sm, const int n0, const int lane) {
+// One warp, one op: 8 rows x 16 right-hand sides of one task, lane (g, q) = row g, columns q, q + 4, q + 8, q + 12
+// (columns 4 q .. 4 q + 3 would put the four q of a B read on one bank for every even leading dimension), on the FP64
+// FMA pipe -- NOT on DMMA.  Measured with cycle stamps inside the op (tools/bush_trace.py, profiles/bush_kernel_r02.txt):
+// a warp that works alone waits ~500 cycles for a DMMA whose accumulator it needs again, so a rank-17 merge (10 k-steps,
+// even spread over four accumulator sets) spent 4000 cycles in its k loops; a dependent DFMA costs a handful of cycles,
+// and the two pipes have the same peak, which these blocks are nowhere near.  Two accumulator sets (even /
+// odd k) halve the FMA chain.  Everything the op reads is normally in shared memory (ALLSM: 32-bit offsets, LDS); a
+// workspace block that could not be staged is read with ld.global.cg -- it was written in this launch by another SM and
+// must not come from a stale L1 line.
+template <bool ALLSM>
+__device__ __forceinline__ void bush_warp_op(const BushOp& o, const CallParams& p, double* sm, const int n0, const int lane, long long* probe) {
+  if (probe && lane == 0) probe[1] = clock64();
   const int g = lane >> 2, q = lane & 3;
   const int N = p.nrhs;
   const int mr = o.mr, m0 = o.m0;
-  const bool two = mr > 8;                    // second m-tile in use
-  const bool cv0 = n0 + g < N, cv1 = n0 + 8 + g < N;
-  const bool rv0 = g < mr, rv1 = 8 + g < mr;
-  double acc[4][2][2][2];
+  const int row = g < mr ? g : mr - 1;         // lanes past the chunk recompute its last row and store nothing
+  double acc[2][4];
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
+  for (int u = 0; u < 2; ++u)
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 2; ++j) acc[u][i][j][0] = acc[u][i][j][1] = 0.0;
+    for (int j = 0; j < 4; ++j) acc[u][j] = 0.0;
+  if (probe && lane == 0) probe[2] = clock64();
 #pragma unroll 1
   for (int s = 0; s < 2; ++s) {
     const int K = s ? o.K1 : o.K0;
@@ -122,52 +123,58 @@ __device__ __forceinline__ void bush_warp_op(const BushOp& o, const CallParams& 
     const bool ta = s ? o.ta1 : o.ta0;
     const int lda = s ? o.lda1 : o.lda0;
     const int sa = s ? o.sa1 : o.sa0;
-    // lane (g, q): A fragment of m-tile i = A[m0 + 8 i + g][k0 + q], B fragment of n-tile j = B[k0 + q][n0 + 8 j + g]
-    const double* pa = (sa >= 0 ? sm + sa : p.pool + (s ? o.a1 : o.a0)) + (ta ? (int64_t)(m0 + g) * lda + q : (int64_t)q * lda + m0 + g);
-    const int64_t a_tile = ta ? (int64_t)8 * lda : 8, a_k = ta ? 1 : (int64_t)lda;
     const int soff = s ? o.s1 : o.s0;
-    const double* pb0;
-    int64_t ldb;
-    const bool bsm = soff >= 0;
-    if (bsm) {
-      pb0 = sm + soff;
-      ldb = s ? o.lds1 : o.lds0;
-    } else {
-      pb0 = operand_b(p, s ? o.sb1 : o.sb0, s ? o.b1 : o.b0, s ? o.ldb1 : o.ldb0, ldb) + (int64_t)n0 * ldb;
-    }
-    pb0 += (int64_t)g * ldb + q;
-    const double* pb1 = pb0 + 8 * ldb;
-#pragma unroll 1
-    for (int kb = 0; kb < K; kb += 16) {
-      double a[4][2], b[4][2];
+    if (ALLSM) {
+      const int ldb = s ? o.lds1 : o.lds0;
+      const int a_k = ta ? 1 : lda;
+      int ia = sa + (ta ? (m0 + row) * lda : m0 + row);
+      int ib = soff + q * ldb;
+      int k = 0;
+#pragma unroll 2
+      for (; k + 1 < K; k += 2) {
+        const double a0 = sm[ia], a1 = sm[ia + a_k];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const int k0 = kb + 4 * u;
-        const bool kin = k0 + q < K;
-        a[u][0] = (rv0 && kin) ? pa[k0 * a_k] : 0.0;
-        a[u][1] = (rv1 && kin) ? pa[a_tile + k0 * a_k] : 0.0;
-        if (bsm) {
-          b[u][0] = (kin && cv0) ? pb0[k0] : 0.0;
-          b[u][1] = (kin && cv1) ? pb1[k0] : 0.0;
-        } else {
-          b[u][0] = (kin && cv0) ? __ldcg(pb0 + k0) : 0.0;
-          b[u][1] = (kin && cv1) ? __ldcg(pb1 + k0) : 0.0;
+        for (int j = 0; j < 4; ++j) {
+          acc[0][j] = fma(a0, sm[ib + 4 * j * ldb], acc[0][j]);
+          acc[1][j] = fma(a1, sm[ib + 4 * j * ldb + 1], acc[1][j]);
         }
+        ia += 2 * a_k; ib += 2;
       }
+      if (k < K) {
+        const double a0 = sm[ia];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (kb + 4 * u < K) {
-          mma_m8n8k4(acc[u][0][0][0], acc[u][0][0][1], a[u][0], b[u][0]);
-          mma_m8n8k4(acc[u][0][1][0], acc[u][0][1][1], a[u][0], b[u][1]);
-          if (two) {
-            mma_m8n8k4(acc[u][1][0][0], acc[u][1][0][1], a[u][1], b[u][0]);
-            mma_m8n8k4(acc[u][1][1][0], acc[u][1][1][1], a[u][1], b[u][1]);
-          }
+        for (int j = 0; j < 4; ++j) acc[0][j] = fma(a0, sm[ib + 4 * j * ldb], acc[0][j]);
+      }
+    } else {
+      const double* pa = (sa >= 0 ? sm + sa : p.pool + (s ? o.a1 : o.a0)) + (ta ? (int64_t)(m0 + row) * lda : (int64_t)(m0 + row));
+      const int64_t a_k = ta ? 1 : (int64_t)lda;
+      const double* pb;
+      int64_t ldb;
+      const bool bsm = soff >= 0;
+      if (bsm) {
+        pb = sm + soff;
+        ldb = s ? o.lds1 : o.lds0;
+      } else {
+        pb = operand_b(p, s ? o.sb1 : o.sb0, s ? o.b1 : o.b0, s ? o.ldb1 : o.ldb0, ldb) + (int64_t)n0 * ldb;
+      }
+      const bool cg = !bsm && (s ? o.sb1 : o.sb0) != SRC_X;
+      bool cv[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) cv[j] = bsm || n0 + q + 4 * j < N;   // global memory ends at column nrhs
+      pb += (int64_t)q * ldb;
+#pragma unroll 1
+      for (int k = 0; k < K; ++k) {
+        const double a0 = pa[k * a_k];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double bv = !cv[j] ? 0.0 : (cg ? __ldcg(pb + 4 * j * ldb + k) : pb[4 * j * ldb + k]);
+          acc[0][j] = fma(a0, bv, acc[0][j]);
         }
       }
     }
   }
-  // lane (g, q) of accumulator (i, j) holds C[8 i + g][8 j + 2 q + {0, 1}]
+  if (probe && lane == 0) probe[3] = clock64();
+  // lane (g, q) holds C[m0 + g][n0 + q + 4 j]
   int64_t ldc = 0;
   double* C = nullptr;
   if (o.to_global) {
@@ -176,32 +183,28 @@ __device__ __forceinline__ void bush_warp_op(const BushOp& o, const CallParams& 
       case SRC_F: ldc = o.ldc; C = p.F + o.c * (int64_t)N; break;
       default: ldc = p.ldy; C = p.Y + o.c; break;
     }
-    C += (int64_t)n0 * ldc + m0;
+    C += (int64_t)(n0 + q) * ldc + m0 + g;
   }
   const int sc_off = o.sc_off, ldsc = o.ldsc;
   const bool epi = o.epilogue;
   const double alpha = p.alpha, beta = p.beta;
+  if (g < mr) {
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int cl = 8 * j + 2 * q + e;
-#pragma unroll
-      for (int i = 0; i < 2; ++i) {
-        const int row = 8 * i + g;
-        if (row >= mr) continue;
-        double v = (acc[0][i][j][e] + acc[1][i][j][e]) + (acc[2][i][j][e] + acc[3][i][j][e]);
-        if (sc_off >= 0) sm[sc_off + cl * ldsc + m0 + row] = v;  // columns past nrhs hold zeros
-        if (C && n0 + cl < N) {
-          double* dst = C + (int64_t)cl * ldc + row;
-          if (epi) {
-            v *= alpha;
-            if (beta != 0.0) v += beta * (*dst);  // beta == 0 never reads Y (matmul.jl:13)
-          }
-          *dst = v;
+    for (int j = 0; j < 4; ++j) {
+      double v = acc[0][j] + acc[1][j];
+      if (probe && lane == 0 && j == 0) probe[4] = v == 12345.678 ? 0 : clock64();
+      if (sc_off >= 0) sm[sc_off + (q + 4 * j) * ldsc + m0 + g] = v;  // columns past nrhs hold whatever the operands held there: never stored
+      if (C && n0 + q + 4 * j < N) {
+        double* dst = C + (int64_t)4 * j * ldc;
+        if (epi) {
+          v *= alpha;
+          if (beta != 0.0) v += beta * (*dst);  // beta == 0 never reads Y (matmul.jl:13)
         }
+        *dst = v;
       }
     }
+  }
+  if (probe && lane == 0) probe[5] = clock64();
 }
 
 __device__ __forceinline__ void bush_stage_issue(const BushStage& st, const BushParams& f, const CallParams& p, double* sm,
@@ -291,9 +294,19 @@ bush_kernel(BushParams f, CallParams p) {
     int o0 = 0;
     for (int l = 0; l < nlevels; ++l) {
       const int o1 = s_hdr.lvl_end[l];
-      for (int o = o0 + warp; o < o1; o += B_WARPS) bush_warp_op(ops[o], p, bush_sm, n0, lane);
+      // diagnostics: cycle stamps of the probed item, per level and warp (level start, op start, k loops start / end,
+      // first accumulator read, op end, after the barrier)
+      long long* probe = (tr && idx == f.probe_item && l < B_PROBE_LEVELS) ? (long long*)(f.trace + (size_t)total * B_TRACE) + (l * B_WARPS + warp) * 8 : nullptr;
+      if (probe && lane == 0) probe[0] = clock64();
+      for (int o = o0 + warp; o < o1; o += B_WARPS) {
+        const BushOp& op = ops[o];
+        if ((op.K0 <= 0 || (op.sa0 >= 0 && op.s0 >= 0)) && (op.K1 <= 0 || (op.sa1 >= 0 && op.s1 >= 0))) bush_warp_op<true>(op, p, bush_sm, n0, lane, probe);
+        else bush_warp_op<false>(op, p, bush_sm, n0, lane, probe);
+      }
       o0 = o1;
+      if (probe && lane == 0) probe[6] = clock64();
       __syncthreads();  // the level's blocks (shared memory, and workspace blocks re-read by this CTA) are complete
+      if (probe && lane == 0) probe[7] = clock64();
       if (tr && tid == 0 && l < 8) tr[3 + l] = bush_now();
     }
     if (tid == 0) {
@@ -478,11 +491,11 @@ static void bush_plan_host(const hssb_matrix* H, int mode, int hb, int ht, int b
     h.st0 = (int32_t)bp.stages.size();
     h.dep0 = (int32_t)bp.deps.size(); h.ndeps = (int32_t)bdeps[(size_t)b].size();
     for (int32_t d : bdeps[(size_t)b]) bp.deps.push_back(newid[(size_t)d]);
-    // row chunks per level: 16 rows per warp, 8 when the level would leave warps idle
-    std::vector<int> chunk_of((size_t)nlev, 16);
+    // row chunks: 8 rows per warp
+    std::vector<int> chunk_of((size_t)nlev, 8);
     int nops = 0;
     for (int l = 0; l < nlev; ++l) {
-      int chunk = 16, n = 0;
+      int chunk = 8, n = 0;
       for (;; chunk >>= 1) {
         n = 0;
         for (int32_t i : ts)
@@ -630,8 +643,8 @@ static int ensure_bush_plan(hssb_matrix* H, int mode, int64_t nrhs) {
     bp->sync_dev = nullptr; bp->sync_cols = 0;
     if (bp->trace_dev) { cudaFree(bp->trace_dev); bp->trace_dev = nullptr; }
     if (H->bush_trace) {
-      HSSB_CUDA(cudaMalloc(&bp->trace_dev, (size_t)bp->nbush * ncol * B_TRACE * sizeof(unsigned long long)));
-      HSSB_CUDA(cudaMemset(bp->trace_dev, 0, (size_t)bp->nbush * ncol * B_TRACE * sizeof(unsigned long long)));
+      HSSB_CUDA(cudaMalloc(&bp->trace_dev, ((size_t)bp->nbush * ncol * B_TRACE + B_PROBE_LEVELS * B_WARPS * 8) * sizeof(unsigned long long)));
+      HSSB_CUDA(cudaMemset(bp->trace_dev, 0, ((size_t)bp->nbush * ncol * B_TRACE + B_PROBE_LEVELS * B_WARPS * 8) * sizeof(unsigned long long)));
     }
     HSSB_CUDA(cudaMalloc(&bp->sync_dev, (size_t)(1 + (int64_t)bp->nbush * ncol) * sizeof(unsigned int)));
     bp->sync_cols = ncol;
@@ -656,6 +669,7 @@ static int launch_bush(hssb_matrix* H, int mode, const CallParams& cp, cudaStrea
   f.ops = bp->ops_dev; f.hdr = bp->hdr_dev; f.stages = bp->stages_dev; f.deps = bp->deps_dev;
   f.sync = bp->sync_dev; f.nbush = bp->nbush;
   f.trace = H->bush_trace && ncol == bp->sync_cols ? bp->trace_dev : nullptr;
+  f.probe_item = H->bush_probe_item;
   const int grid = (int)std::min<int64_t>((int64_t)bp->nbush * ncol, bp->grid_cap);
   bush_kernel<<<grid, B_THREADS, (size_t)bp->smem_doubles * sizeof(double), st>>>(f, cp);
   H->launches++;

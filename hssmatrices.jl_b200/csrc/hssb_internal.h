@@ -251,11 +251,13 @@ struct hssb_matrix {
   // HSSB_OPT_FLOW_KERNEL: any-shape plans of single-shard handles run as ONE persistent dataflow kernel (hssb_flow.cuh)
   int flow_kernel = 1;
   void* flow_plan[2] = {nullptr, nullptr};  // [0] Y = A X, [1] Y = A' X on the any-shape task table
-  // HSSB_OPT_BUSH_KERNEL: small any-shape trees (64-row leaves, ranks <= 64: what a compression produces) run as ONE launch
-  // whose items are whole bushes of the tree (hssb_bush.cuh).  0 off, 1 automatic (eligible trees), 2 whenever a plan exists
-  int bush_kernel = 1;
-  int bush_levels = 3, bush_levels0 = 2;    // HSSB_OPT_BUSH_LEVELS: levels per bush / levels of the bushes that hold the leaves
+  // HSSB_OPT_BUSH_KERNEL: the merge / translate levels of small any-shape trees (64-row leaves, ranks <= 64: what a compression
+  // produces) as ONE launch whose items are whole bushes of the tree (hssb_bush.cuh).  0 off (default: measured slower than the
+  // dataflow kernel, profiles/bush_kernel_r02.txt), 1 eligible trees, 2 whenever a plan exists
+  int bush_kernel = 0;
+  int bush_levels = 2, bush_levels0 = 1;    // HSSB_OPT_BUSH_LEVELS: levels per bush / merge levels of the bush that holds the root
   void* bush_plan[2] = {nullptr, nullptr};
+  int bush_probe_item = 0;                  // ... and cycle stamps inside the ops of this item
   bool bush_trace = false;                  // hssb_debug_bush_trace: the kernel records a timeline per item
   void* tree_plan = nullptr;
 };

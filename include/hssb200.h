@@ -250,13 +250,15 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
                                     the 2*depth+2 dependent levels cost a flag round trip each instead of a launch (csrc/hssb_flow.cuh).
                                     Single-shard handles, product and transposed product.  0: one launch per level.  hssb_get_option
                                     returns 2 once the product plan has been set up for it                                          */
-#define HSSB_OPT_BUSH_KERNEL 16  /* 1 (default): SMALL any-shape trees (leaves of at most 64 rows / columns, ranks <= 64, at most 16384
-                                    leaves: BASELINE configs 1-2) run the whole product in one launch whose work items are BUSHES -- the
-                                    tasks of a few consecutive levels below one node -- executed by one CTA with the intermediate Z / F
-                                    blocks in shared memory; the dependent chain of config 2 is 7 flag round trips instead of 22 levels
-                                    (csrc/hssb_bush.cuh).  Takes precedence over HSSB_OPT_FLOW_KERNEL where it applies.  2: any
-                                    single-shard any-shape plan.  0: off.  hssb_get_option returns 3 once the product plan runs on it   */
-#define HSSB_OPT_BUSH_LEVELS 17  /* levels per bush * 16 + levels of the bushes that hold the leaves (default 3 * 16 + 2); rebuilds the plan */
+#define HSSB_OPT_BUSH_KERNEL 16  /* 0 (default).  1: SMALL any-shape trees (leaves of at most 64 rows / columns, ranks <= 64, at most 16384
+                                    leaves: BASELINE configs 1-2) run every merge / translate level between the two leaf launches as ONE
+                                    launch whose work items are BUSHES -- the tasks of a few consecutive levels below one node --
+                                    executed by one CTA out of shared memory (bulk-copy staging, warp-sized tasks, flags between bushes
+                                    only: 10 dependent steps for config 2 instead of 20 levels; csrc/hssb_bush.cuh).  2: any single-shard
+                                    any-shape plan.  Takes precedence over HSSB_OPT_FLOW_KERNEL where it applies.  Parity-tested; measured
+                                    SLOWER than the dataflow kernel (config-2 shape: 225 us against 196 us, profiles/bush_kernel_r02.txt),
+                                    hence off by default.  hssb_get_option returns 3 once the product plan runs on it                   */
+#define HSSB_OPT_BUSH_LEVELS 17  /* levels per bush * 16 + merge levels of the bush that holds the root (default 2 * 16 + 1); rebuilds the plan */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */

@@ -147,7 +147,7 @@ def run_bush_plan(packed, X, Y, alpha=1.0, beta=0.0, trans=False):
             pending = []
             for o in levels[l]:
                 t = st.tasks[o.task]
-                assert 0 <= o.m0 and 0 < o.mr <= 16 and o.m0 + o.mr <= t.M
+                assert 0 <= o.m0 and 0 < o.mr <= 8 and o.m0 + o.mr <= t.M
                 acc = np.zeros((o.mr, N))
                 for s in range(2):
                     K = t.K1 if s else t.K0

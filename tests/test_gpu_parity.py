@@ -515,10 +515,9 @@ def test_dataflow_kernel_any_shape_trees(gpu, oracle, n, leafsize, nrhs, rmin, r
 def test_bush_kernel_small_trees(gpu, oracle, n, leafsize, nrhs, rmin, rmax, levels):
     """Small any-shape trees (BASELINE configs 1-2): every merge / translate level between the two leaf launches
     runs as ONE launch over whole bushes of the tree (HSSB_OPT_BUSH_KERNEL, csrc/hssb_bush.cuh): a few levels of
-    matmul.jl:39 / :52-56 per CTA out of shared memory, warp-sized DMMA tasks.  Same k order and the same DMMA as
-    the any-shape tile kernel but four interleaved accumulator sets (a warp working alone is bound by the latency of a
-    dependent DMMA): agrees with one launch per level to rounding, and with itself bit for bit; also A' X on the
-    transposed task table, alpha / beta, repeated calls, other cuts of the tree (HSSB_OPT_BUSH_LEVELS) and, forced (= 2), a tree
+    matmul.jl:39 / :52-56 per CTA out of shared memory, warp-sized tasks
+    (on the FP64 FMA pipe: a warp working alone is bound by the latency of a dependent DMMA): agrees with one launch per
+    level to rounding, and with itself bit for bit; also A' X on the transposed task table, alpha / beta, repeated calls, other cuts of the tree (HSSB_OPT_BUSH_LEVELS) and, forced (= 2), a tree
     with 128-row leaves."""
     rng = np.random.default_rng(n + nrhs)
     rcl = oracle.bisection_cluster(n, leafsize)

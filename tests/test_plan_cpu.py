@@ -106,7 +106,8 @@ def test_bush_plan_matches_oracle(hb, oracle, n, leafsize, nrhs, rmin, rmax, lev
     depth = int(P.info.depth)
     if depth >= 6 and levels == 3 * 16 + 2:
         assert st["chain"] <= 2 * ((depth + 2) // 3) + 1 < 2 * depth   # the point of the exercise
-        assert st["staged_a"] == st["staged_b"] == st["ops"]              # nothing on a bush's critical path reads global memory
+    if levels == 2 * 16 + 1:
+        assert st["staged_a"] == st["staged_b"] == st["ops"]           # default cut: nothing on a bush's critical path reads global memory
     Y = np.full((n, nrhs), np.nan, order="F")
     plan_interp.run_bush_plan(P, X, Y, trans=True)
     assert relerr(Y, oracle.matmul(oracle.adjoint(h), X)) <= TOL

@@ -17,7 +17,8 @@ for name, n, leaf, rmin, rmax, k in (("c1-like", 2001, 64, 9, 20, 16), ("c2-like
     P.set_option(hb.OPT_FLOW_KERNEL, 0)
     if len(sys.argv) > 1:
         P.set_option(hb.OPT_BUSH_LEVELS, int(sys.argv[1]))
-    P.debug_bush_trace()
+    probe = int(os.environ.get('PROBE', '0'))
+    P.debug_bush_trace(probe_item=probe)
     X = torch.randn((k, n), dtype=torch.float64, device="cuda"); Y = torch.empty_like(X)
     for _ in range(5):
         P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=s.cuda_stream)
@@ -44,4 +45,11 @@ for name, n, leaf, rmin, rmax, k in (("c1-like", 2001, 64, 9, 20, 16), ("c2-like
         print(f"  step {d}: {m.sum()} items, drawn {(r[:, 1].min() - t0) / 1e3:.1f}..{(r[:, 1].max() - t0) / 1e3:.1f} us, deps met {(r[:, 2].min() - t0) / 1e3:.1f}..{(r[:, 2].max() - t0) / 1e3:.1f},"
               f" wait med {np.median(r[:, 2] - r[:, 1]) / 1e3:.1f}, levels med us {np.round(np.median(ends - prev, axis=0) / 1e3, 2).tolist()},"
               f" publish med {np.median(r[:, 11] - ends[:, -1]) / 1e3:.2f}, done {(r[:, 11].min() - t0) / 1e3:.1f}..{(r[:, 11].max() - t0) / 1e3:.1f}")
+    pr = P.bush_probe
+    print(f"  probe item {probe} (cycles; per level and warp: op start, k loops start, k loops end, first accumulator read, op end, before barrier, after barrier -- relative to level start)")
+    for l in range(8):
+        if pr[l].any():
+            for w in range(8):
+                if pr[l, w, 0]:
+                    print(f"    level {l} warp {w}:", [int(x - pr[l, w, 0]) if x else None for x in pr[l, w, 1:]])
     P.close()
