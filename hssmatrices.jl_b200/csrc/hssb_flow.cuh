@@ -159,9 +159,14 @@ flow_kernel(FlowParams f, CallParams p) {
           const double* ap = ta ? As + (wm + g) * G_SB + q4 : As + q4 * G_SA + wm + g;
           const int a_tile = ta ? 8 * G_SB : 8, a_step = ta ? 4 : 4 * G_SA;
           const double* bp = Bs + (wn + g) * G_SB + q4;
+          // k-steps past the end of the operand are zero fill: skipping them changes nothing in the result (x + 0 * 0)
+          // and takes them off the chain of DEPENDENT DMMAs, ~500 cycles each for a warp that has nothing else in
+          // flight (profiles/bush_kernel_r02.txt) -- a rank-17 operand is 5 k-steps, not 8
+          const int ks_end = ((slab >= nslab0 ? K1 - (slab - nslab0) * G_TK : K0 - slab * G_TK) + 3) >> 2;
           if (active) {
 #pragma unroll
             for (int ks = 0; ks < G_TK / 4; ++ks) {
+              if (ks >= ks_end) break;
               double a[4], b[2];
 #pragma unroll
               for (int i = 0; i < 4; ++i) a[i] = ap[ks * a_step + i * a_tile];
