@@ -30,4 +30,16 @@ P = hb.pack(to_product_tree(hb, h))
 print("flow", rel(P @ X, o.matmul(h, X)), "A'X", rel(P.tmatmul(X), o.matmul(o.adjoint(h), X)))
 P.set_option(hb.OPT_FLOW_KERNEL, 0)
 print("levels", rel(P @ X, o.matmul(h, X)))
+P.set_option(hb.OPT_BUSH_KERNEL, 1)   # merge / translate levels as one launch over bushes of the tree
+for lv in (2 * 16 + 1, 3 * 16 + 2):
+    P.set_option(hb.OPT_BUSH_LEVELS, lv)
+    print("bush", lv, rel(P @ X, o.matmul(h, X)), "A'X", rel(P.tmatmul(X), o.matmul(o.adjoint(h), X)), "in use:", P.get_option(hb.OPT_BUSH_KERNEL) == 3)
+P.close()
+cl = o.bisection_cluster(4096, 64)
+h = o.random_hss(cl, cl, rng, 13, 40)    # config-2 shape, ranks up to 40: some blocks exceed the shared-memory budget
+X = rng.standard_normal((4096, 33))
+P = hb.pack(to_product_tree(hb, h))
+P.set_option(hb.OPT_BUSH_KERNEL, 1)
+P.set_option(hb.OPT_BUSH_LEVELS, 3 * 16 + 2)
+print("bush 4096/64 ranks 13-40", rel(P @ X, o.matmul(h, X)))
 P.close()
