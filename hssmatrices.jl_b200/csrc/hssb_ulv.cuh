@@ -61,25 +61,47 @@ struct Mat {
 };
 HSSB_HD Mat colmajor(double* p, int64_t ld) { return Mat{p, 1, ld}; }
 HSSB_HD Mat colmajor(const double* p, int64_t ld) { return Mat{const_cast<double*>(p), 1, ld}; }
+HSSB_HD Mat rowmajor(double* p, int64_t ld) { return Mat{p, ld, 1}; }
 
 // C (M x N) = alpha * A (M x K) * B (K x N) + beta * C   (beta == 0 never reads C)
+// One thread per 4 x 2 block of C: six loads feed eight FMAs per k (one thread per element needed two loads per FMA, and
+// the factorisation is bound by exactly that: ncu on the leaf level of config 3 shows 183 MB of L1 load traffic per node,
+// 0.57 IPC per SM).  Eight independent accumulation chains per thread.
 HSSB_HD void tm_gemm(const Team& tm, Mat C, Mat A, Mat B, int M, int N, int K, double alpha, double beta) {
   // C never overlaps A or B (callers pass distinct blocks): without __restrict__ every store to C
   // would order the following loads behind it
-  const int64_t total = (int64_t)M * N;
+  const int nbi = (M + 3) / 4, nbj = (N + 1) / 2;
+  const int64_t total = (int64_t)nbi * nbj;
   for (int64_t e = tm.tid; e < total; e += tm.nt) {
-    const int i = (int)(e % M), j = (int)(e / M);
-    const double* __restrict__ a = A.p + i * A.rs;
-    const double* __restrict__ b = B.p + j * B.cs;
-    double s0 = 0.0, s1 = 0.0;
-    int kk = 0;
-    for (; kk + 1 < K; kk += 2) {  // two independent accumulation chains
-      s0 = fma(a[kk * A.cs], b[kk * B.rs], s0);
-      s1 = fma(a[(kk + 1) * A.cs], b[(kk + 1) * B.rs], s1);
+    const int i0 = (int)(e % nbi) * 4, j0 = (int)(e / nbi) * 2;
+    const double* __restrict__ a[4];
+    const double* __restrict__ b[2];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) a[ii] = A.p + (i0 + ii < M ? i0 + ii : M - 1) * A.rs;   // rows past the edge: recomputed, never stored
+#pragma unroll
+    for (int jj = 0; jj < 2; ++jj) b[jj] = B.p + (j0 + jj < N ? j0 + jj : N - 1) * B.cs;
+    double s[4][2];
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii) s[ii][0] = s[ii][1] = 0.0;
+    for (int kk = 0; kk < K; ++kk) {
+      double av[4], bv[2];
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii) av[ii] = a[ii][kk * A.cs];
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj) bv[jj] = b[jj][kk * B.rs];
+#pragma unroll
+      for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+        for (int jj = 0; jj < 2; ++jj) s[ii][jj] = fma(av[ii], bv[jj], s[ii][jj]);
     }
-    if (kk < K) s0 = fma(a[kk * A.cs], b[kk * B.rs], s0);
-    const double sum = s0 + s1;
-    C(i, j) = beta == 0.0 ? alpha * sum : alpha * sum + beta * C(i, j);
+#pragma unroll
+    for (int ii = 0; ii < 4; ++ii)
+#pragma unroll
+      for (int jj = 0; jj < 2; ++jj)
+        if (i0 + ii < M && j0 + jj < N) {
+          double& c = C(i0 + ii, j0 + jj);
+          c = beta == 0.0 ? alpha * s[ii][jj] : alpha * s[ii][jj] + beta * c;
+        }
   }
   tm.sync();
 }
@@ -260,11 +282,13 @@ HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double*
   const Mat Din = colmajor(take(MI * NI), m > 0 ? m : 1);
   const Mat Dq = colmajor(take(MI * NI), m > 0 ? m : 1);
   const Mat L2 = colmajor(take(MI * NI), k > 0 ? k : 1);
-  const Mat Uin = colmajor(take(MI * KR), m > 0 ? m : 1);
+  // the matrices tm_qr updates with ONE THREAD PER COLUMN are stored row-major: consecutive threads then touch consecutive
+  // addresses in every step of the reflector loop (column-major, a warp's load hit 32 different cache lines for 32 doubles)
+  const Mat Uin = rowmajor(take(MI * KR), kr > 0 ? kr : 1);
   const Mat Vin = colmajor(take(NI * KW), n > 0 ? n : 1);
   const Mat Vq = colmajor(take(NI * KW), n > 0 ? n : 1);
-  const Mat Q = colmajor(take(MI * MI), m > 0 ? m : 1);
-  const Mat P = colmajor(take(NI * NI), n > 0 ? n : 1);
+  const Mat Q = rowmajor(take(MI * MI), m > 0 ? m : 1);
+  const Mat P = rowmajor(take(NI * NI), n > 0 ? n : 1);
   const Mat T = colmajor(take((MI + KW) * MI), m + kw > 0 ? m + kw : 1);
   const Mat G12 = colmajor(take(MI * KX), u.k1 > 0 ? u.k1 : 1);
   const Mat G21 = colmajor(take(MI * KX), u.k2 > 0 ? u.k2 : 1);
@@ -367,7 +391,7 @@ HSSB_HD void ulv_factor_node(const Team& tm, const UlvCtx& cx, int node, double*
 }
 
 // One CTA per node of one level (grid-stride); scratch is per CTA.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 ulv_factor_kernel(UlvCtx cx, const int32_t* __restrict__ level_nodes, int count, double* scratch, int64_t scratch_stride) {
   const Team tm{(int)threadIdx.x, (int)blockDim.x};
   double* s = scratch + (int64_t)blockIdx.x * scratch_stride;
@@ -378,7 +402,7 @@ ulv_factor_kernel(UlvCtx cx, const int32_t* __restrict__ level_nodes, int count,
 }
 
 // the same for a plan in fast form (HSSB_OPT_ULV_FAST)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 ulv_factor_kernel_ff(UlvCtx cx, const int32_t* __restrict__ level_nodes, int count, double* scratch, int64_t scratch_stride) {
   const Team tm{(int)threadIdx.x, (int)blockDim.x};
   double* s = scratch + (int64_t)blockIdx.x * scratch_stride;

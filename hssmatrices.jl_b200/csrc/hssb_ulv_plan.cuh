@@ -352,8 +352,10 @@ static int ulv_factor_device(hssb_matrix* H, bool adjoint = false) {
     HSSB_FAIL(HSSB_ERR_ALLOC, "device allocation of the %.3f GB ULV factor pool failed", pool_b * 1e-9);
   }
   const auto levels = ulv_levels(H);
-  // per level: scratch per CTA and CTAs in flight (three per SM: 80 registers x 256 threads; fewer when the
-  // scratch of large nodes would not fit in 8 GiB)
+  // per level: scratch per CTA and CTAs in flight (three per SM: 80 registers x 256 threads; four for the fast form's
+  // instantiation, 64 registers -- the kernel is latency-bound, ncu: 0.57 IPC per SM with 37 % of the warp slots in use;
+  // fewer when the scratch of large nodes would not fit in 8 GiB)
+  const size_t ctas_per_sm = H->ulv_ff ? 4 : 3;
   struct LevelRun { UlvLevelDims d; int64_t stride; int ctas; };
   std::vector<LevelRun> runs;
   size_t scratch_doubles = 1;
@@ -361,7 +363,7 @@ static int ulv_factor_device(hssb_matrix* H, bool adjoint = false) {
     LevelRun r;
     r.d = ulv_level_dims(H, l);
     r.stride = round_up(ulv_scratch_len(r.d.MI, r.d.NI, r.d.KR, r.d.KW), 16);
-    r.ctas = (int)std::min<size_t>(std::max<size_t>(l.size(), 1), 148 * 3);
+    r.ctas = (int)std::min<size_t>(std::max<size_t>(l.size(), 1), 148 * ctas_per_sm);
     while (r.ctas > 1 && (size_t)r.ctas * (size_t)r.stride * 8 > ((size_t)8 << 30)) r.ctas /= 2;
     scratch_doubles = std::max(scratch_doubles, (size_t)r.ctas * (size_t)r.stride);
     runs.push_back(r);
