@@ -68,7 +68,7 @@ constexpr int B_MAXLEV = 16;
 struct BushHdr {
   int32_t op0, nops, nlevels;
   int32_t dep0, ndeps;     // bushes whose flags this one waits for
-  int32_t st0, nst_pre, nst_post;  // staged copies issued before the wait (ops, generators, X) and after it (workspace tiles)
+  int32_t st0, nst_pre, nst_post;  // staged copies issued before the wait (ops, generators) and after it (workspace tiles)
   int32_t ops_dst;         // shared-memory copy of the ops (doubles), -1: read from global memory
   int32_t pre_bytes;       // bytes of the copies issued before the wait
   int32_t post_ld;         // sum of the leading dimensions of the workspace tiles (bytes = post_ld * valid columns * 8)
