@@ -1065,6 +1065,10 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
       break;
     case HSSB_OPT_LEAF_FUSION: h->leaf_fusion = value != 0; break;
     case HSSB_OPT_FLOW_KERNEL: h->flow_kernel = value != 0; break;
+    case HSSB_OPT_PDL:
+      if (value < 0 || value > 2) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_PDL: 0, 1 or 2");
+      h->pdl = (int)value;
+      break;
     case HSSB_OPT_BUSH_KERNEL:
       if (value < 0 || value > 2) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_BUSH_KERNEL: 0, 1 or 2");
       h->bush_kernel = (int)value;
@@ -1132,6 +1136,7 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
       return bp && bp->usable && bp->sync_dev && (h->bush_kernel >= 2 || bush_eligible(h)) ? 3 : h->bush_kernel;
     }
     case HSSB_OPT_BUSH_LEVELS: return h->bush_levels * 16 + h->bush_levels0;
+    case HSSB_OPT_PDL: return h->pdl;
     case HSSB_OPT_LAST_BOUNCE: return h->last_bounce;
     case HSSB_OPT_HOST_THREADS: return host_pool(0).size();
     default: return -1;

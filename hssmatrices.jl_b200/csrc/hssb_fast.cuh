@@ -89,6 +89,16 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
                : "memory");
 }
 
+// Programmatic dependent launch (HSSB_OPT_PDL): a kernel launched with the attribute may START while its predecessor in
+// the stream is still running -- its CTAs are placed as soon as every CTA of the predecessor has passed
+// launch_dependents or exited -- and blocks in griddepcontrol.wait until the predecessor has completed and its memory
+// is visible.  Every kernel of the level schedule does both first thing, so the order of the schedule is unchanged; what
+// goes away is the drain / launch gap between the 27 kernels of a product (and whatever a kernel does before its wait:
+// barrier initialisation, the bulk copies of generator blocks, which nobody produces).  Without the attribute both
+// instructions are no-ops.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+
 // n-index of a DMMA tile -> right-hand side within its 8-column group (see stream_leaf_kernel)
 __device__ __forceinline__ int perm8(int n) { return (0x74216530u >> (4 * n)) & 7; }
 
@@ -422,6 +432,8 @@ struct NodeCfg {
 template <int R, int NT_>
 __global__ void __launch_bounds__(288, NodeCfg<R, NT_>::CTAS_PER_SM)
 stream_node_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p) {
+  pdl_launch_dependents();
+  pdl_wait();
   using C = NodeCfg<R, NT_>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double* Bt = reinterpret_cast<double*>(smem_raw);            // [2 buffers][2 operands][NT][LD]
@@ -562,18 +574,20 @@ oneshot_node_kernel(const GTask* __restrict__ tasks, CallParams p) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
   const bool two = tk.K1 > 0;
   const int64_t toff = (int64_t)tile * C::NT * C::LD;
+  pdl_launch_dependents();
+  constexpr uint32_t ab = R * C::LD * 8;
+  const uint32_t bb = (uint32_t)(ncols * C::LD * 8);
   if (tid == 0) {
     mbar_init(bar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-    constexpr uint32_t ab = R * C::LD * 8;
-    const uint32_t bb = (uint32_t)(ncols * C::LD * 8);
     mbar_expect_tx(bar, two ? 2 * (ab + bb) : ab + bb);
-    bulk_g2s(As, p.pool + tk.a0, ab, bar);
+    bulk_g2s(As, p.pool + tk.a0, ab, bar);              // generators: nobody produces them, they travel before the wait
+    if (two) bulk_g2s(As + R * C::LD, p.pool + tk.a1, ab, bar);
+  }
+  pdl_wait();                                           // the level before this one is complete and visible from here on
+  if (tid == 0) {
     bulk_g2s(Bs, (tk.sb0 == SRC_F ? p.F : p.Z) + tk.b0 * (int64_t)nrhs + toff, bb, bar);
-    if (two) {
-      bulk_g2s(As + R * C::LD, p.pool + tk.a1, ab, bar);
-      bulk_g2s(Bs + C::NT * C::LD, (tk.sb1 == SRC_F ? p.F : p.Z) + tk.b1 * (int64_t)nrhs + toff, bb, bar);
-    }
+    if (two) bulk_g2s(Bs + C::NT * C::LD, (tk.sb1 == SRC_F ? p.F : p.Z) + tk.b1 * (int64_t)nrhs + toff, bb, bar);
   }
   __syncthreads();  // the barrier is initialised before anyone polls it
   mbar_wait(bar, 0);
@@ -615,6 +629,23 @@ oneshot_node_kernel(const GTask* __restrict__ tasks, CallParams p) {
 }
 
 // ================================================================ host side ===
+// Kernel launch with or without the programmatic-dependent-launch attribute (HSSB_OPT_PDL: 1 = the one-shot node kernels,
+// where it pays -- many small launches, generator blocks fetched before the wait; 2 = the persistent leaf and node kernels
+// as well, measured neutral to 4 % slower there, tools/pdl_compare.py).
+template <typename... KArgs, typename... Args>
+static cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  memset(at, 0, sizeof(at));
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, (KArgs)args...);
+}
+
 struct FastState {
   int num_sms = 148;
   std::vector<const void*> configured;  // kernels whose dynamic shared-memory limit has been raised on this device
@@ -701,7 +732,7 @@ static int launch_leaf2(hssb_matrix* H, const Phase& ph, const CallParams& cp, c
   const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
   if (int rc = make_x_map(&xmap, cp.X, H->local_n, cp.nrhs, cp.ldx, C::NT)) return rc;
   if (int rc = fs->configure((const void*)leaf2_kernel<M, R, DOWN, NT, KC>, C::SMEM)) return rc;
-  leaf2_kernel<M, R, DOWN, NT, KC><<<grid, C::NWARPS * 32 + 32, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp, xmap);
+  HSSB_CUDA(launch_k(H->pdl > 1, leaf2_kernel<M, R, DOWN, NT, KC>, dim3(grid), dim3(C::NWARPS * 32 + 32), C::SMEM, st, (const GTask*)(H->tasks_dev + ph.task0), (int)ph.ntasks, ntiles, cp, xmap));
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
   return HSSB_OK;
@@ -758,7 +789,7 @@ static int launch_node_nt(hssb_matrix* H, const Phase& ph, const CallParams& cp,
   const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
   const int grid = (int)std::min<int64_t>(ph.ntasks * ntiles, (int64_t)fs->num_sms * C::CTAS_PER_SM);
   if (int rc = fs->configure((const void*)stream_node_kernel<R, NT>, C::SMEM)) return rc;
-  stream_node_kernel<R, NT><<<grid, 288, C::SMEM, st>>>(H->tasks_dev + ph.task0, (int)ph.ntasks, ntiles, cp);
+  HSSB_CUDA(launch_k(H->pdl > 1, stream_node_kernel<R, NT>, dim3(grid), dim3(288), C::SMEM, st, (const GTask*)(H->tasks_dev + ph.task0), (int)ph.ntasks, ntiles, cp));
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
   return HSSB_OK;
@@ -771,7 +802,7 @@ static int launch_node(hssb_matrix* H, const Phase& ph, const CallParams& cp, cu
       using C = OneShotCfg<R>;
       FastState* fs = (FastState*)H->fast_state;
       if (int rc = fs->configure((const void*)oneshot_node_kernel<R>, C::SMEM)) return rc;
-      oneshot_node_kernel<R><<<dim3((unsigned)ph.ntasks, 1), 128, C::SMEM, st>>>(H->tasks_dev + ph.task0, cp);
+      HSSB_CUDA(launch_k(H->pdl > 0, oneshot_node_kernel<R>, dim3((unsigned)ph.ntasks, 1), dim3(128), C::SMEM, st, (const GTask*)(H->tasks_dev + ph.task0), cp));
       H->launches++;
       HSSB_CUDA(cudaGetLastError());
       return HSSB_OK;

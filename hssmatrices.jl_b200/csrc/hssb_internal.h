@@ -4,10 +4,15 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdlib.h>
 #include <string>
 #include <vector>
 
 #include "../../include/hssb200.h"
+
+#ifndef HSSB_PDL_DEFAULT
+#define HSSB_PDL_DEFAULT 1
+#endif
 
 namespace hssb {
 
@@ -142,6 +147,14 @@ struct Phase {
 
 }  // namespace hssb
 
+namespace hssb {
+// default of HSSB_OPT_PDL: the environment variable HSSB_PDL (0 / 1) overrides the built-in default for every new handle
+inline int default_pdl() {
+  static const int v = [] { const char* e = getenv("HSSB_PDL"); const int x = e ? atoi(e) : HSSB_PDL_DEFAULT; return x < 0 ? 0 : (x > 2 ? 2 : x); }();
+  return v;
+}
+}  // namespace hssb
+
 // The opaque handle of the public ABI.
 struct hssb_matrix {
   int device = 0;
@@ -248,6 +261,9 @@ struct hssb_matrix {
   // HSSB_OPT_LEAF_FUSION: 1 = the "X once" variant (hssb_leafx.cuh): leaf-up forms D X and V' X in one pass over X and
   // parks alpha D X + beta Y in Y, leaf-down adds alpha U F.  Measured slower than the two-pass default.
   int leaf_fusion = 0;
+  // HSSB_OPT_PDL: 1 (default) the one-shot node kernels of the level schedule are launched with programmatic stream serialisation
+  // (hssb_fast.cuh), 2 the persistent leaf / node kernels as well (measured neutral to slower), 0 plain stream order
+  int pdl = hssb::default_pdl();
   // HSSB_OPT_FLOW_KERNEL: any-shape plans of single-shard handles run as ONE persistent dataflow kernel (hssb_flow.cuh)
   int flow_kernel = 1;
   void* flow_plan[2] = {nullptr, nullptr};  // [0] Y = A X, [1] Y = A' X on the any-shape task table

@@ -57,6 +57,8 @@ leaf2_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams
   uint64_t* f_full = bars + 2 * C::NSTAGE;
   uint64_t* f_empty = f_full + 1;
 
+  pdl_launch_dependents();  // HSSB_OPT_PDL (hssb_fast.cuh): the next kernel of the schedule may be placed while this one runs ...
+  pdl_wait();               // ... and this one touches nothing before its predecessor is complete
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int nitems = ntasks * ntiles;
   const int first = (int)(((int64_t)blockIdx.x * nitems) / gridDim.x);
