@@ -1066,7 +1066,7 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
     case HSSB_OPT_LEAF_FUSION: h->leaf_fusion = value != 0; break;
     case HSSB_OPT_FLOW_KERNEL: h->flow_kernel = value != 0; break;
     case HSSB_OPT_PDL:
-      if (value < 0 || value > 2) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_PDL: 0, 1 or 2");
+      if (value < 0 || value > 7) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_PDL: bits 0-2");
       h->pdl = (int)value;
       break;
     case HSSB_OPT_BUSH_KERNEL:

@@ -433,7 +433,6 @@ template <int R, int NT_>
 __global__ void __launch_bounds__(288, NodeCfg<R, NT_>::CTAS_PER_SM)
 stream_node_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, CallParams p) {
   pdl_launch_dependents();
-  pdl_wait();
   using C = NodeCfg<R, NT_>;
   extern __shared__ __align__(1024) unsigned char smem_raw[];
   double* Bt = reinterpret_cast<double*>(smem_raw);            // [2 buffers][2 operands][NT][LD]
@@ -474,9 +473,8 @@ stream_node_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
       bulk_g2s(Bt + (buf * 2) * C::TILE, ws(tk.sb0) + tk.b0 * (int64_t)nrhs + toff, bytes, &b_full[buf]);
       if (two) bulk_g2s(Bt + (buf * 2 + 1) * C::TILE, ws(tk.sb1) + tk.b1 * (int64_t)nrhs + toff, bytes, &b_full[buf]);
     };
-    load_b(0);
     int g = 0;
-    for (int item = 0; item < my; ++item) {
+    auto load_a = [&](int item) {
       const GTask& tk = tasks[(first + item) / ntiles];
       for (int c = 0; c < nch; ++c, ++g) {
         const int st = g % C::NSTAGE;
@@ -484,6 +482,12 @@ stream_node_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
         mbar_expect_tx(&a_full[st], C::STAGE * 8);
         bulk_g2s(As + st * C::STAGE, p.pool + (c ? tk.a1 : tk.a0), C::STAGE * 8, &a_full[st]);
       }
+    };
+    load_a(0);   // generator blocks: nobody produces them, they travel before the wait (HSSB_OPT_PDL)
+    pdl_wait();  // the previous level is complete and visible from here on
+    load_b(0);
+    for (int item = 0; item < my; ++item) {
+      if (item > 0) load_a(item);
       // in order of need: this item's A blocks first, then the next item's B tiles (their buffer
       // frees up when the consumers leave item-1)
       if (item + 1 < my) load_b(item + 1);
@@ -492,6 +496,7 @@ stream_node_kernel(const GTask* __restrict__ tasks, int ntasks, int ntiles, Call
   }
 
   // ====================== consumer warps ======================
+  pdl_wait();  // they only read what the producer fetched after ITS wait; this one orders their stores as well
   const int gq = lane >> 2, t = lane & 3;
   const int wr = warp % C::WR, wc = warp / C::WR;
   double acc[C::TM][C::TN][2];
@@ -629,9 +634,10 @@ oneshot_node_kernel(const GTask* __restrict__ tasks, CallParams p) {
 }
 
 // ================================================================ host side ===
-// Kernel launch with or without the programmatic-dependent-launch attribute (HSSB_OPT_PDL: 1 = the one-shot node kernels,
-// where it pays -- many small launches, generator blocks fetched before the wait; 2 = the persistent leaf and node kernels
-// as well, measured neutral to 4 % slower there, tools/pdl_compare.py).
+// Kernel launch with or without the programmatic-dependent-launch attribute.  HSSB_OPT_PDL bits: 1 = where it was measured
+// to pay (tools/pdl_compare.py, profiles/pdl_r02.txt): the one-shot node kernels (config 3: -1.8 %) and the persistent node
+// kernel at rank 64, one CTA per SM (config 5 shape -3 %, config 4 shape -0.8 %); 2 = every persistent node kernel (rank 32,
+// two CTAs per SM: +1 %); 4 = the leaf kernels (+2 .. 6 %).
 template <typename... KArgs, typename... Args>
 static cudaError_t launch_k(bool pdl, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
   cudaLaunchConfig_t cfg;
@@ -732,7 +738,7 @@ static int launch_leaf2(hssb_matrix* H, const Phase& ph, const CallParams& cp, c
   const int grid = std::min((int)ph.ntasks * ntiles, fs->num_sms);
   if (int rc = make_x_map(&xmap, cp.X, H->local_n, cp.nrhs, cp.ldx, C::NT)) return rc;
   if (int rc = fs->configure((const void*)leaf2_kernel<M, R, DOWN, NT, KC>, C::SMEM)) return rc;
-  HSSB_CUDA(launch_k(H->pdl > 1, leaf2_kernel<M, R, DOWN, NT, KC>, dim3(grid), dim3(C::NWARPS * 32 + 32), C::SMEM, st, (const GTask*)(H->tasks_dev + ph.task0), (int)ph.ntasks, ntiles, cp, xmap));
+  HSSB_CUDA(launch_k((H->pdl & 4) != 0, leaf2_kernel<M, R, DOWN, NT, KC>, dim3(grid), dim3(C::NWARPS * 32 + 32), C::SMEM, st, (const GTask*)(H->tasks_dev + ph.task0), (int)ph.ntasks, ntiles, cp, xmap));
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
   return HSSB_OK;
@@ -789,7 +795,7 @@ static int launch_node_nt(hssb_matrix* H, const Phase& ph, const CallParams& cp,
   const int ntiles = (cp.nrhs + C::NT - 1) / C::NT;
   const int grid = (int)std::min<int64_t>(ph.ntasks * ntiles, (int64_t)fs->num_sms * C::CTAS_PER_SM);
   if (int rc = fs->configure((const void*)stream_node_kernel<R, NT>, C::SMEM)) return rc;
-  HSSB_CUDA(launch_k(H->pdl > 1, stream_node_kernel<R, NT>, dim3(grid), dim3(288), C::SMEM, st, (const GTask*)(H->tasks_dev + ph.task0), (int)ph.ntasks, ntiles, cp));
+  HSSB_CUDA(launch_k((H->pdl & 2) != 0 || ((H->pdl & 1) != 0 && R >= 64), stream_node_kernel<R, NT>, dim3(grid), dim3(288), C::SMEM, st, (const GTask*)(H->tasks_dev + ph.task0), (int)ph.ntasks, ntiles, cp));
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
   return HSSB_OK;
@@ -802,7 +808,7 @@ static int launch_node(hssb_matrix* H, const Phase& ph, const CallParams& cp, cu
       using C = OneShotCfg<R>;
       FastState* fs = (FastState*)H->fast_state;
       if (int rc = fs->configure((const void*)oneshot_node_kernel<R>, C::SMEM)) return rc;
-      HSSB_CUDA(launch_k(H->pdl > 0, oneshot_node_kernel<R>, dim3((unsigned)ph.ntasks, 1), dim3(128), C::SMEM, st, (const GTask*)(H->tasks_dev + ph.task0), cp));
+      HSSB_CUDA(launch_k((H->pdl & 1) != 0, oneshot_node_kernel<R>, dim3((unsigned)ph.ntasks, 1), dim3(128), C::SMEM, st, (const GTask*)(H->tasks_dev + ph.task0), cp));
       H->launches++;
       HSSB_CUDA(cudaGetLastError());
       return HSSB_OK;

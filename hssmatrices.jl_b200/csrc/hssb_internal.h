@@ -150,7 +150,7 @@ struct Phase {
 namespace hssb {
 // default of HSSB_OPT_PDL: the environment variable HSSB_PDL (0 / 1) overrides the built-in default for every new handle
 inline int default_pdl() {
-  static const int v = [] { const char* e = getenv("HSSB_PDL"); const int x = e ? atoi(e) : HSSB_PDL_DEFAULT; return x < 0 ? 0 : (x > 2 ? 2 : x); }();
+  static const int v = [] { const char* e = getenv("HSSB_PDL"); const int x = e ? atoi(e) : HSSB_PDL_DEFAULT; return x < 0 ? 0 : (x > 7 ? 7 : x); }();
   return v;
 }
 }  // namespace hssb
@@ -261,8 +261,8 @@ struct hssb_matrix {
   // HSSB_OPT_LEAF_FUSION: 1 = the "X once" variant (hssb_leafx.cuh): leaf-up forms D X and V' X in one pass over X and
   // parks alpha D X + beta Y in Y, leaf-down adds alpha U F.  Measured slower than the two-pass default.
   int leaf_fusion = 0;
-  // HSSB_OPT_PDL: 1 (default) the one-shot node kernels of the level schedule are launched with programmatic stream serialisation
-  // (hssb_fast.cuh), 2 the persistent leaf / node kernels as well (measured neutral to slower), 0 plain stream order
+  // HSSB_OPT_PDL (bits): 1 (default) the node kernels of the level schedule are launched with programmatic stream serialisation
+  // where it pays (hssb_fast.cuh: launch_k), 2 every persistent node kernel, 4 the leaf kernels (measured slower), 0 plain stream order
   int pdl = hssb::default_pdl();
   // HSSB_OPT_FLOW_KERNEL: any-shape plans of single-shard handles run as ONE persistent dataflow kernel (hssb_flow.cuh)
   int flow_kernel = 1;

@@ -259,13 +259,14 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
                                     SLOWER than the dataflow kernel (config-2 shape: 225 us against 196 us, profiles/bush_kernel_r02.txt),
                                     hence off by default.  hssb_get_option returns 3 once the product plan runs on it                   */
 #define HSSB_OPT_BUSH_LEVELS 17  /* levels per bush * 16 + merge levels of the bush that holds the root (default 2 * 16 + 1); rebuilds the plan */
-#define HSSB_OPT_PDL 18          /* 1 (default; environment HSSB_PDL overrides): the one-shot node kernels of a uniform tree's level schedule
-                                    (rank <= 32, 32 < nrhs <= 64: the 25 merge / translate launches of config 3) are launched with
-                                    programmatic dependent launch: a kernel's CTAs are placed while its predecessor still runs, fetch
-                                    their generator blocks, and wait (griddepcontrol.wait) until the predecessor has completed -- no
-                                    drain / launch gap between the small levels; same order, bit-identical results (config 3 -1.8 %,
-                                    n = 2^16 -5 %).  2: the persistent leaf and node kernels as well (measured neutral to 6 % slower).
-                                    0: plain stream order                                                                          */
+#define HSSB_OPT_PDL 18          /* bits; 1 (default; environment HSSB_PDL overrides): the node kernels of a uniform tree's level schedule are
+                                    launched with programmatic dependent launch where that was measured to pay -- the one-shot kernels
+                                    (rank <= 32, 32 < nrhs <= 64: the 25 merge / translate launches of config 3) and the persistent
+                                    node kernel at rank 64: a kernel's CTAs are placed while its predecessor still runs, fetch their
+                                    generator blocks, and wait (griddepcontrol.wait) until the predecessor has completed -- no drain /
+                                    launch gap between the levels; same order, bit-identical results (config 3 -1.8 %, config-5 shape
+                                    -3 %, n = 2^16 -5 %).  2: every persistent node kernel, 4: the leaf kernels as well (measured
+                                    slower).  0: plain stream order                                                                */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
