@@ -677,7 +677,10 @@ def main():
             by_s = ui.flops_per_rhs // 2 * 8 + 2 * 8 * rows * k
             solve = {"what": "Z = A \\ X (hssb_solve_dev, ULV factors resident, device time per call)", "ms_per_solve": ms_solve,
                      "gflops": fl_s / ms_solve * 1e-6, "flops": fl_s, "algorithmic_bytes": by_s, "hbm_gbs": by_s / ms_solve * 1e-6,
-                     "factor_ms_once": t_factor * 1e3, "factor_pool_gb": ui.pool_bytes * 1e-9,
+                     "factor_ms_once": t_factor * 1e3, "factor_device_ms": P.get_option(hb.OPT_LAST_FACTOR_US) * 1e-3,
+                     "factor_note": "factor_ms_once is the wall time of hssb_ulv_factor in this process (it allocates and clears the factor pool and "
+                                    "its scratch beside torch's cached blocks); factor_device_ms is the device time of its kernels (CUDA events)",
+                     "factor_pool_gb": ui.pool_bytes * 1e-9,
                      "fast_form": P.get_option(hb.OPT_ULV_FAST) == 2,
                      "relative_residual": resid, "steps": steps_s,
                      "note": "||A Z - X|| / ||X|| with A Z from the product path; the synthetic matrix is ill conditioned "

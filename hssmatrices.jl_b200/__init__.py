@@ -157,7 +157,7 @@ SIGNATURES = {
     "hssb_group_sync": (C.c_int, [_P]),
 }
 
-OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS, OPT_ADJOINT_TWIN, OPT_ULV_FAST, OPT_TREE_KERNEL, OPT_HOST_BOUNCE, OPT_LAST_BOUNCE, OPT_LEAF_KERNEL, OPT_LEAF_FUSION, OPT_FLOW_KERNEL, OPT_HOST_THREADS, OPT_BUSH_KERNEL, OPT_BUSH_LEVELS, OPT_PDL = 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18
+OPT_FORCE_GENERIC, OPT_USE_GRAPH, OPT_PROFILE, OPT_DEBUG, OPT_PIPELINE_COLS, OPT_ADJOINT_TWIN, OPT_ULV_FAST, OPT_TREE_KERNEL, OPT_HOST_BOUNCE, OPT_LAST_BOUNCE, OPT_LEAF_KERNEL, OPT_LEAF_FUSION, OPT_FLOW_KERNEL, OPT_HOST_THREADS, OPT_BUSH_KERNEL, OPT_BUSH_LEVELS, OPT_PDL, OPT_LAST_FACTOR_US = 1, 2, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19
 PHASE_NAMES = ("leaf_up", "merge", "exchange", "translate", "leaf_down", "exchange_ack")
 KIND_NAMES = ("D", "U", "V", "B12", "B21", "R", "W")
 

@@ -1137,6 +1137,7 @@ int64_t hssb_get_option(const hssb_matrix* h, int opt) {
     }
     case HSSB_OPT_BUSH_LEVELS: return h->bush_levels * 16 + h->bush_levels0;
     case HSSB_OPT_PDL: return h->pdl;
+    case HSSB_OPT_LAST_FACTOR_US: return h->ulv_last_factor_us;
     case HSSB_OPT_LAST_BOUNCE: return h->last_bounce;
     case HSSB_OPT_HOST_THREADS: return host_pool(0).size();
     default: return -1;

@@ -175,6 +175,7 @@ struct hssb_matrix {
   bool ulv_t_factored = false;
   std::vector<double> ulv_pool_host;  // plan-only handles: factorised on the host by the test hook
   bool ulv_factored = false;
+  int64_t ulv_last_factor_us = 0;     // device time of the level launches of the last factorisation (HSSB_OPT_LAST_FACTOR_US)
   bool ulv_fast_form = true;          // HSSB_OPT_ULV_FAST (default on since it ran green on hardware: solve 2.60 -> 1.79 ms on config 3)
   bool ulv_ff = false;                // ... and the tree qualifies: the ULV plan is in fast form
   int64_t ulv_task0 = -1;             // first ULV task in tasks_host (the ULV plan can be rebuilt)

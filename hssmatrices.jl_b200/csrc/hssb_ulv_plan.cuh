@@ -384,6 +384,10 @@ static int ulv_factor_device(hssb_matrix* H, bool adjoint = false) {
   std::vector<int32_t> flat;
   for (auto& l : levels) flat.insert(flat.end(), l.begin(), l.end());
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_list, flat.data(), flat.size() * sizeof(int32_t), cudaMemcpyHostToDevice, H->stream);
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;   // device time of the level launches alone (HSSB_OPT_LAST_FACTOR_US): the wall time of
+  if (e == cudaSuccess) e = cudaEventCreate(&ev0);   // this call also holds the allocation and clearing of a multi-GB pool
+  if (e == cudaSuccess) e = cudaEventCreate(&ev1);
+  if (e == cudaSuccess) e = cudaEventRecord(ev0, H->stream);
   if (e == cudaSuccess) {
     size_t at = 0;
     for (size_t li = 0; li < levels.size(); ++li) {
@@ -400,8 +404,15 @@ static int ulv_factor_device(hssb_matrix* H, bool adjoint = false) {
     }
     e = cudaGetLastError();
   }
+  if (e == cudaSuccess) e = cudaEventRecord(ev1, H->stream);
   if (e == cudaSuccess) e = cudaMemcpyAsync(pivmin.data(), d_piv, pivmin.size() * sizeof(double), cudaMemcpyDeviceToHost, H->stream);
   if (e == cudaSuccess) e = cudaStreamSynchronize(H->stream);
+  if (e == cudaSuccess) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, ev0, ev1) == cudaSuccess) H->ulv_last_factor_us = (int64_t)(ms * 1e3f);
+  }
+  if (ev0) cudaEventDestroy(ev0);
+  if (ev1) cudaEventDestroy(ev1);
   cleanup();
   if (e != cudaSuccess) {
     cudaFree(fpool_dev);

@@ -267,6 +267,8 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
                                     launch gap between the levels; same order, bit-identical results (config 3 -1.8 %, config-5 shape
                                     -3 %, n = 2^16 -5 %).  2: every persistent node kernel, 4: the leaf kernels as well (measured
                                     slower).  0: plain stream order                                                                */
+#define HSSB_OPT_LAST_FACTOR_US 19 /* read-only: device time (microseconds, CUDA events) of the level launches of the last ULV factorisation;
+                                    the wall time of hssb_ulv_factor also holds the allocation and clearing of the factor pool       */
 int hssb_set_option(hssb_matrix* h, int opt, int64_t value);
 int64_t hssb_get_option(const hssb_matrix* h, int opt);
 /* Kernels launched by this handle since creation (for bench.py's gpu_launches). */
