@@ -487,8 +487,6 @@ def run_small_tree_extra(ctx, what, n, leaf, rmin, rmax, k, steps, peaks):
             P.set_option(hb.OPT_USE_GRAPH, 1)
             for _ in range(3):
                 P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=st)
-            if name == "default":
-                default_kernel = "bush" if P.get_option(hb.OPT_BUSH_KERNEL) == 3 else ("flow" if P.get_option(hb.OPT_FLOW_KERNEL) == 2 else "levels")
             l0 = P.launch_count()
             ts = []
             for _ in range(steps):
@@ -504,8 +502,9 @@ def run_small_tree_extra(ctx, what, n, leaf, rmin, rmax, k, steps, peaks):
         fl, by = P.flops(k), P.algorithmic_bytes(k)
         ms = res["default"][0]
         t_mem, t_flop = by / (peaks["hbm"] * 1e9) * 1e3, fl / (peaks["fp64"] * 1e12) * 1e3
+        default_kernel = "bush" if res["default"][1] == 3 else ("flow" if res["default"][1] == 1 else "levels")
         kernels = {"bush": "leaf-up launch, every merge / translate level as one launch over bushes of the tree (csrc/hssb_bush.cuh), leaf-down launch",
-                   "flow": "persistent dataflow kernel (csrc/hssb_flow.cuh)", "levels": "one launch per level"}
+                   "flow": "persistent dataflow kernel (csrc/hssb_flow.cuh)", "levels": "one launch per level with programmatic dependent launch (the library's choice under graph replay)"}
         ref = res["levels"][2]
         out = {"workload": what, "n": n, "leafsize": leaf, "ranks": [rmin, rmax], "nrhs": k, "value": fl / ms * 1e-6, "unit": "GFLOP/s",
                "hbm_gbs": by / ms * 1e-6, "ms_per_step": ms, "steps": steps, "timing": "median of per-product CUDA-event times, L2 flushed between products",
@@ -514,7 +513,7 @@ def run_small_tree_extra(ctx, what, n, leaf, rmin, rmax, k, steps, peaks):
                                      "rel_diff_to_level_launches": float((res[nm][2] - ref).norm() / ref.norm())} for nm in ("levels", "flow", "bush")},
                "product_roofline": {"flops": fl, "algorithmic_bytes": by, "t_mem_ms": t_mem, "t_flop_ms": t_flop,
                                     "binding": "tensor" if t_flop >= t_mem else "hbm", "frac_of_roofline": max(t_mem, t_flop) / ms,
-                                    "note": "latency-bound: 2*depth+2 dependent levels; the bush kernel cuts the chain to ~2*depth/3 flag round trips"}}
+                                    "note": "latency-bound: 2*depth+2 dependent levels"}}
         P.close()
         del flush
         torch.cuda.empty_cache()

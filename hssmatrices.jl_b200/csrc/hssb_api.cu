@@ -237,7 +237,7 @@ namespace hssb {
 static int launch_generic(hssb_matrix* H, const Phase& ph, const CallParams& cp, cudaStream_t st) {
   if (ph.ntasks == 0) return HSSB_OK;
   dim3 grid((unsigned)ph.ntasks, (unsigned)((ph.maxM + G_TM - 1) / G_TM), (unsigned)((cp.nrhs + G_TN - 1) / G_TN));
-  generic_level_kernel<<<grid, G_THREADS, 0, st>>>(H->tasks_dev + ph.task0, cp);
+  HSSB_CUDA(launch_k((H->pdl & 9) != 0, generic_level_kernel, grid, dim3(G_THREADS), 0, st, (const GTask*)(H->tasks_dev + ph.task0), cp));
   H->launches++;
   HSSB_CUDA(cudaGetLastError());
   return HSSB_OK;
@@ -271,7 +271,9 @@ static int run_phases(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
     }
     return HSSB_OK;
   }
-  if (flow_usable(H, cp.trans) && plan_runs_generic(H, cp)) return launch_flow(H, cp.trans, cp, st);
+  // (automatic, HSSB_OPT_FLOW_KERNEL = 2: only for plain launches -- replayed as a CUDA graph, one launch per level with
+  // programmatic dependent launch is faster: config-2 shape 170 us against 194 us, profiles/pdl_r02.txt)
+  if (flow_usable(H, cp.trans) && (H->flow_kernel == 1 || !H->capturing) && plan_runs_generic(H, cp)) return launch_flow(H, cp.trans, cp, st);
   if (prof) {
     H->prof_mode = cp.trans;
     while (H->prof_events.size() < phases.size() + 1) {
@@ -393,7 +395,9 @@ static int run_graph(hssb_matrix* H, const CallParams& cp, cudaStream_t st) {
   // capture on the library's own stream (the legacy default stream cannot be captured),
   // replay on the caller's stream
   HSSB_CUDA(cudaStreamBeginCapture(H->stream, cudaStreamCaptureModeThreadLocal));
+  H->capturing = true;
   int rc = run_phases(H, cp, H->stream);
+  H->capturing = false;
   cudaError_t e = cudaStreamEndCapture(H->stream, &graph);
   const int64_t kernels = H->launches - before;
   H->launches = before;
@@ -1064,9 +1068,12 @@ int hssb_set_option(hssb_matrix* h, int opt, int64_t value) {
       h->leaf_kernel = (int)value;
       break;
     case HSSB_OPT_LEAF_FUSION: h->leaf_fusion = value != 0; break;
-    case HSSB_OPT_FLOW_KERNEL: h->flow_kernel = value != 0; break;
+    case HSSB_OPT_FLOW_KERNEL:
+      if (value < 0 || value > 2) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_FLOW_KERNEL: 0, 1 or 2");
+      h->flow_kernel = (int)value;
+      break;
     case HSSB_OPT_PDL:
-      if (value < 0 || value > 7) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_PDL: bits 0-2");
+      if (value < 0 || value > 15) HSSB_FAIL(HSSB_ERR_ARG, "HSSB_OPT_PDL: bits 0-3");
       h->pdl = (int)value;
       break;
     case HSSB_OPT_BUSH_KERNEL:

@@ -96,8 +96,7 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
 // goes away is the drain / launch gap between the 27 kernels of a product (and whatever a kernel does before its wait:
 // barrier initialisation, the bulk copies of generator blocks, which nobody produces).  Without the attribute both
 // instructions are no-ops.
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+// (pdl_launch_dependents / pdl_wait: hssb_kernels_generic.cuh)
 
 // n-index of a DMMA tile -> right-hand side within its 8-column group (see stream_leaf_kernel)
 __device__ __forceinline__ int perm8(int n) { return (0x74216530u >> (4 * n)) & 7; }

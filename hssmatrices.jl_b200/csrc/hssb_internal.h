@@ -150,7 +150,7 @@ struct Phase {
 namespace hssb {
 // default of HSSB_OPT_PDL: the environment variable HSSB_PDL (0 / 1) overrides the built-in default for every new handle
 inline int default_pdl() {
-  static const int v = [] { const char* e = getenv("HSSB_PDL"); const int x = e ? atoi(e) : HSSB_PDL_DEFAULT; return x < 0 ? 0 : (x > 7 ? 7 : x); }();
+  static const int v = [] { const char* e = getenv("HSSB_PDL"); const int x = e ? atoi(e) : HSSB_PDL_DEFAULT; return x < 0 ? 0 : (x > 15 ? 15 : x); }();
   return v;
 }
 }  // namespace hssb
@@ -266,7 +266,8 @@ struct hssb_matrix {
   // where it pays (hssb_fast.cuh: launch_k), 2 every persistent node kernel, 4 the leaf kernels (measured slower), 0 plain stream order
   int pdl = hssb::default_pdl();
   // HSSB_OPT_FLOW_KERNEL: any-shape plans of single-shard handles run as ONE persistent dataflow kernel (hssb_flow.cuh)
-  int flow_kernel = 1;
+  int flow_kernel = 2;   // 0 never, 1 always, 2 automatic: for plain launches; under CUDA-graph capture one launch per level (with HSSB_OPT_PDL) is faster
+  bool capturing = false;  // run_graph is capturing the schedule
   void* flow_plan[2] = {nullptr, nullptr};  // [0] Y = A X, [1] Y = A' X on the any-shape task table
   // HSSB_OPT_BUSH_KERNEL: the merge / translate levels of small any-shape trees (64-row leaves, ranks <= 64: what a compression
   // produces) as ONE launch whose items are whole bushes of the tree (hssb_bush.cuh).  0 off (default: measured slower than the

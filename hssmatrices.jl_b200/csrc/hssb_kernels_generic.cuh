@@ -11,6 +11,12 @@
 #include "hssb_mma.cuh"
 
 namespace hssb {
+// programmatic dependent launch (HSSB_OPT_PDL, see hssb_fast.cuh); no-ops for kernels launched without the attribute
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;\n" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;\n" ::: "memory"); }
+}  // namespace hssb
+
+namespace hssb {
 
 constexpr int G_TM = 64, G_TN = 64, G_TK = 16, G_THREADS = 256;
 
@@ -37,7 +43,7 @@ static_assert(G_TK * G_SA <= G_SMEM, "k-major image must fit");
 // One 64 x 64 output tile (rows m0.., right-hand sides n0..) of one task.  WS_CG: operands from the Z / F
 // workspaces are read with ld.global.cg (L2 only) -- needed when the producer of the block ran in the SAME launch
 // on another SM (hssb_flow.cuh), where a stale L1 line would be a wrong answer.
-template <bool WS_CG>
+template <bool WS_CG, bool PDL = false>
 __device__ __forceinline__ void generic_tile(const GTask& t, const int m0, const int n0, const CallParams& p, double* As, double* Bs) {
   const int N = p.nrhs;
   const int tid = threadIdx.x;
@@ -65,15 +71,12 @@ __device__ __forceinline__ void generic_tile(const GTask& t, const int m0, const
   const double* B0 = operand_b(p, t.sb0, t.b0, t.ldb0, ldb0);
   const double* B1 = operand_b(p, t.sb1, t.b1, t.ldb1, ldb1);
   double ra[4], rb[4];
-  auto fetch = [&](int slab) {
+  auto fetch_a = [&](int slab) {
     const bool s1 = slab >= nslab0;
     const int K = s1 ? K1 : K0, k0 = (s1 ? slab - nslab0 : slab) * G_TK;
     const double* A = p.pool + (s1 ? t.a1 : t.a0);
     const int64_t lda = s1 ? t.lda1 : t.lda0;
     const bool ta = s1 ? t.ta1 : t.ta0;
-    const double* B = s1 ? B1 : B0;
-    const int64_t ldb = s1 ? ldb1 : ldb0;
-    const bool ws = WS_CG && (s1 ? t.sb1 : t.sb0) != SRC_X;
     if (!ta) {
       const int mm = tid & 63;
 #pragma unroll
@@ -89,6 +92,13 @@ __device__ __forceinline__ void generic_tile(const GTask& t, const int m0, const
         ra[r] = (m0 + mm < t.M && k0 + kk < K) ? A[(int64_t)(m0 + mm) * lda + (k0 + kk)] : 0.0;
       }
     }
+  };
+  auto fetch_b = [&](int slab) {
+    const bool s1 = slab >= nslab0;
+    const int K = s1 ? K1 : K0, k0 = (s1 ? slab - nslab0 : slab) * G_TK;
+    const double* B = s1 ? B1 : B0;
+    const int64_t ldb = s1 ? ldb1 : ldb0;
+    const bool ws = WS_CG && (s1 ? t.sb1 : t.sb0) != SRC_X;
     const int kk = tid & 15;
 #pragma unroll
     for (int r = 0; r < 4; ++r) {
@@ -98,6 +108,7 @@ __device__ __forceinline__ void generic_tile(const GTask& t, const int m0, const
       rb[r] = in ? (ws ? __ldcg(src) : *src) : 0.0;
     }
   };
+  auto fetch = [&](int slab) { fetch_a(slab); fetch_b(slab); };
   auto stage = [&](int slab) {  // registers -> shared memory, same element mapping as fetch()
     const bool ta = slab >= nslab0 ? t.ta1 : t.ta0;
     if (!ta) {
@@ -111,7 +122,11 @@ __device__ __forceinline__ void generic_tile(const GTask& t, const int m0, const
     for (int r = 0; r < 4; ++r) Bs[((tid >> 4) + 16 * r) * G_SB + (tid & 15)] = rb[r];
   };
 
-  if (nslab > 0) fetch(0);
+  // HSSB_OPT_PDL (hssb_fast.cuh): launched with the attribute, the CTA is placed while the previous level still runs; the first
+  // slab of the generator block -- which nobody produces -- travels before the wait, everything else after it
+  if (nslab > 0) fetch_a(0);
+  if (PDL) pdl_wait();
+  if (nslab > 0) fetch_b(0);
   for (int slab = 0; slab < nslab; ++slab) {
     stage(slab);
     __syncthreads();
@@ -174,10 +189,11 @@ __global__ void __launch_bounds__(G_THREADS, 3)
 generic_level_kernel(const GTask* __restrict__ tasks, CallParams p) {
   __shared__ double As[G_SMEM];
   __shared__ double Bs[G_SMEM];
+  pdl_launch_dependents();
   const GTask t = tasks[blockIdx.x];
   const int m0 = blockIdx.y * G_TM;
   if (m0 >= t.M) return;
-  generic_tile<false>(t, m0, blockIdx.z * G_TN, p, As, Bs);
+  generic_tile<false, true>(t, m0, blockIdx.z * G_TN, p, As, Bs);
 }
 
 }  // namespace hssb

@@ -244,12 +244,15 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
                                     stacked operand) and parks alpha D X + beta Y in Y, leaf-down adds alpha U F.  Uniform trees with
                                     (leaf, rank) in {(128,32), (128,64)}; other shapes keep the default.  Same results to
                                     rounding; measured slower (Y is written twice and read once more), kept as the measured alternative */
-#define HSSB_OPT_FLOW_KERNEL 14  /* 1 (default): trees no fixed-shape kernel applies to (ragged leaves, variable ranks: every matrix that
-                                    comes out of a compression) run the WHOLE product as one persistent dataflow kernel: tasks are drawn
-                                    from a queue in level order and wait on per-task counters for the producers of their operands, so
-                                    the 2*depth+2 dependent levels cost a flag round trip each instead of a launch (csrc/hssb_flow.cuh).
-                                    Single-shard handles, product and transposed product.  0: one launch per level.  hssb_get_option
-                                    returns 2 once the product plan has been set up for it                                          */
+#define HSSB_OPT_FLOW_KERNEL 14  /* trees no fixed-shape kernel applies to (ragged leaves, variable ranks: every matrix that comes out of a
+                                    compression) can run the WHOLE product as one persistent dataflow kernel: tasks are drawn from a
+                                    queue in level order and wait on per-task counters for the producers of their operands, so the
+                                    2*depth+2 dependent levels cost a flag round trip each instead of a launch (csrc/hssb_flow.cuh).
+                                    Single-shard handles, product and transposed product.  2 (default): automatic -- the dataflow
+                                    kernel for plain launches; when the schedule is replayed as a CUDA graph (the host entry, or
+                                    HSSB_OPT_USE_GRAPH) one launch per level with programmatic dependent launch is faster (config-2
+                                    shape 170 us against 194 us) and is used instead.  1: always.  0: never.  hssb_get_option returns
+                                    2 once the product plan has been set up for it                                                  */
 #define HSSB_OPT_BUSH_KERNEL 16  /* 0 (default).  1: SMALL any-shape trees (leaves of at most 64 rows / columns, ranks <= 64, at most 16384
                                     leaves: BASELINE configs 1-2) run every merge / translate level between the two leaf launches as ONE
                                     launch whose work items are BUSHES -- the tasks of a few consecutive levels below one node --
@@ -261,11 +264,11 @@ int hssb_ulv_info(const hssb_matrix* h, hssb_ulv_info_t* out);
 #define HSSB_OPT_BUSH_LEVELS 17  /* levels per bush * 16 + merge levels of the bush that holds the root (default 2 * 16 + 1); rebuilds the plan */
 #define HSSB_OPT_PDL 18          /* bits; 1 (default; environment HSSB_PDL overrides): the node kernels of a uniform tree's level schedule are
                                     launched with programmatic dependent launch where that was measured to pay -- the one-shot kernels
-                                    (rank <= 32, 32 < nrhs <= 64: the 25 merge / translate launches of config 3) and the persistent
-                                    node kernel at rank 64: a kernel's CTAs are placed while its predecessor still runs, fetch their
+                                    (rank <= 32, 32 < nrhs <= 64: the 25 merge / translate launches of config 3), the persistent
+                                    node kernel at rank 64 and the any-shape tile kernel (one launch per level): a kernel's CTAs are placed while its predecessor still runs, fetch their
                                     generator blocks, and wait (griddepcontrol.wait) until the predecessor has completed -- no drain /
                                     launch gap between the levels; same order, bit-identical results (config 3 -1.8 %, config-5 shape
-                                    -3 %, n = 2^16 -5 %).  2: every persistent node kernel, 4: the leaf kernels as well (measured
+                                    -3 %, n = 2^16 -5 %, config-2 shape -10 %).  2: every persistent node kernel, 4: the leaf kernels (measured
                                     slower).  0: plain stream order                                                                */
 #define HSSB_OPT_LAST_FACTOR_US 19 /* read-only: device time (microseconds, CUDA events) of the level launches of the last ULV factorisation;
                                     the wall time of hssb_ulv_factor also holds the allocation and clearing of the factor pool       */

@@ -506,6 +506,20 @@ def test_dataflow_kernel_any_shape_trees(gpu, oracle, n, leafsize, nrhs, rmin, r
     assert relerr(got, oracle.mul(C0.copy(), h, X, 0.7, -1.3)) <= TOL
     X2 = rng.standard_normal((n, 2 * nrhs + 1))       # more column tiles than before: the counters grow
     assert relerr(P @ X2, oracle.matmul(h, X2)) <= TOL
+    # automatic (the default): the host entry replays a CUDA graph, where one launch per level with programmatic dependent
+    # launch is the faster schedule; plain launches on caller-owned device arrays take the dataflow kernel
+    P.set_option(gpu.OPT_FLOW_KERNEL, 2)
+    l0 = P.launch_count()
+    Y2 = P @ X
+    assert P.launch_count() - l0 == per_level and np.array_equal(Y2, Y0)
+    import torch
+    Xd = torch.from_numpy(np.ascontiguousarray(X.T)).cuda()
+    Yd = torch.empty_like(Xd)
+    st = torch.cuda.current_stream().cuda_stream
+    l0 = P.launch_count()
+    P.matmul_dev(Xd.data_ptr(), n, Yd.data_ptr(), n, nrhs, stream=st)
+    torch.cuda.synchronize()
+    assert P.launch_count() - l0 == 1 and np.array_equal(Yd.cpu().numpy().T, Y0)
     P.close()
 
 

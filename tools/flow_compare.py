@@ -21,11 +21,16 @@ for name, n, leaf, rmin, rmax, k in (("c1-like n=2001 leaf 64 ranks 9-20", 2001,
     variants = [(0, 0, 50), (1, 0, 50), (0, 1, 50), (0, 1, 2 * 16 + 1), (0, 1, 2 * 16 + 2), (0, 1, 3 * 16 + 3), (0, 1, 4 * 16 + 2), (0, 1, 3 * 16 + 1), (0, 1, 50), (1, 0, 50)]
     if len(sys.argv) > 1 and sys.argv[1] == "quick":
         variants = [(1, 0, 50), (0, 1, 50)]
+    if len(sys.argv) > 1 and sys.argv[1] == "pdl":   # level launches with / without programmatic dependent launch against the dataflow kernel
+        variants = [(1, 0, 1), (0, 0, 1), (0, 0, 9), (1, 0, 1), (0, 0, 1), (0, 0, 9)]
     Yref = None
     for flow, bush, levels in variants:
         P.set_option(hb.OPT_FLOW_KERNEL, flow)
         P.set_option(hb.OPT_BUSH_KERNEL, bush)
-        P.set_option(hb.OPT_BUSH_LEVELS, levels)
+        if len(sys.argv) > 1 and sys.argv[1] == "pdl":
+            P.set_option(hb.OPT_PDL, levels)
+        else:
+            P.set_option(hb.OPT_BUSH_LEVELS, levels)
         for _ in range(3):
             P.matmul_dev(X.data_ptr(), n, Y.data_ptr(), n, k, stream=s.cuda_stream)
         l0 = P.launch_count()
@@ -38,7 +43,7 @@ for name, n, leaf, rmin, rmax, k in (("c1-like n=2001 leaf 64 ranks 9-20", 2001,
         if Yref is None:
             Yref = Y.clone()
         same = float((Y - Yref).norm() / Yref.norm())
-        out.append((("bush %d/%d" % (levels // 16, levels % 16)) if bush else ("flow" if flow else "levels"), (P.launch_count() - l0) // 50, round(ms * 1e3, 1), same))
+        out.append((("bush %d/%d" % (levels // 16, levels % 16)) if bush else ("flow" if flow else ("levels pdl %d" % P.get_option(hb.OPT_PDL))), (P.launch_count() - l0) // 50, round(ms * 1e3, 1), same))
     t_flop, t_mem = fl / 37.1e12, by / 6.4686e12
     print(f"{name}: flops {fl:.3e} bytes {by:.3e} roofline {max(t_flop, t_mem) * 1e6:.1f} us | (kernel, launches, us, rel. difference to the first):", out)
     P.close()
